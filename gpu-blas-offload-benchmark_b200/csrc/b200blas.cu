@@ -1,0 +1,486 @@
+// b200blas.cu -- the extern "C" ABI of libb200blas.so (see include/b200blas.h):
+// context, cached allocation, asynchronous copy lanes with explicit event
+// ordering, kernel dispatch and the Always-mode transfer engine.
+//
+// Ordering model.  The reference relies on legacy-default-stream semantics:
+// s1_..s3_ are blocking streams and cuBLAS runs on the NULL stream, so the GEMM
+// implicitly waits for the three uploads and the D2H on s3_ implicitly waits
+// for the GEMM (cuBLAS/gemm.hh:60-62,126-150).  Here every stream is
+// non-blocking and the same ordering is explicit:
+//   upload on lane L   -> record lane_done[L], mark lane_pending[L]
+//   compute call       -> compute stream waits on every pending lane event
+//   download on lane L -> lane waits on an event recorded after the last kernel
+// so back-to-back kernels in Once mode cost one launch each and nothing else.
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace b200 {
+
+static thread_local char g_error[512] = "no error";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+int ensure_workspace(b200_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->workspace_bytes) return 0;
+  // the old workspace may still be in use by queued kernels
+  B200_CUDA(cudaStreamSynchronize(ctx->compute));
+  if (ctx->workspace) B200_CUDA(cudaFree(ctx->workspace));
+  ctx->workspace = nullptr;
+  ctx->workspace_bytes = 0;
+  size_t cap = std::max(bytes + bytes / 4, (size_t)(8u << 20));
+  B200_CUDA(cudaMalloc(&ctx->workspace, cap));
+  ctx->workspace_bytes = cap;
+  return 0;
+}
+
+int join_lanes_into_compute(b200_ctx* ctx) {
+  for (int l = 0; l < B200_NUM_LANES; l++) {
+    if (ctx->lane_pending[l]) {
+      B200_CUDA(cudaStreamWaitEvent(ctx->compute, ctx->lane_done[l], 0));
+      ctx->lane_pending[l] = false;
+    }
+  }
+  return 0;
+}
+
+// A copy lane must not overtake kernels that still read/write the buffer.
+static int lanes_wait_for_compute(b200_ctx* ctx) {
+  if (!ctx->compute_unordered) return 0;
+  B200_CUDA(cudaEventRecord(ctx->compute_done, ctx->compute));
+  for (int l = 0; l < B200_NUM_LANES; l++)
+    B200_CUDA(cudaStreamWaitEvent(ctx->lane[l], ctx->compute_done, 0));
+  ctx->compute_unordered = false;
+  return 0;
+}
+
+static size_t round_capacity(size_t bytes) {
+  const size_t min_gran = 64u << 10;
+  if (bytes <= min_gran) return min_gran;
+  size_t p = 1;
+  while (p * 2 <= bytes) p *= 2;
+  const size_t gran = std::max(min_gran, p / 8);
+  return (bytes + gran - 1) / gran * gran;
+}
+
+static void* cache_take(std::vector<CachedBlock>& cache, size_t cap) {
+  for (size_t i = 0; i < cache.size(); i++) {
+    if (cache[i].capacity == cap) {
+      void* p = cache[i].ptr;
+      cache.erase(cache.begin() + i);
+      return p;
+    }
+  }
+  return nullptr;
+}
+
+template <typename FreeFn>
+static void cache_put(std::vector<CachedBlock>& cache, void* p, size_t cap,
+                      size_t max_total, FreeFn free_fn) {
+  if (cap > max_total) {
+    free_fn(p);
+    return;
+  }
+  cache.push_back({p, cap});
+  size_t total = 0;
+  for (auto& b : cache) total += b.capacity;
+  while (cache.size() > 12 || total > max_total) {
+    total -= cache.front().capacity;
+    free_fn(cache.front().ptr);
+    cache.erase(cache.begin());
+  }
+}
+
+// capacity bookkeeping for live blocks (ptr -> capacity)
+static size_t live_pop(std::vector<CachedBlock>& v, void* p) {
+  for (size_t i = 0; i < v.size(); i++)
+    if (v[i].ptr == p) {
+      const size_t c = v[i].capacity;
+      v.erase(v.begin() + i);
+      return c;
+    }
+  return 0;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+const char* b200_last_error(void) { return g_error; }
+const char* b200_version(void) { return "b200blas 0.1 (sm_100a)"; }
+
+int b200_ctx_create(b200_ctx** out, int device) {
+  B200_REQUIRE(out != nullptr, "b200_ctx_create: out is null");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    set_error("b200_ctx_create: no CUDA device (%s); this library has no CPU fallback",
+              e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    return 1;
+  }
+  if (device < 0) B200_CUDA(cudaGetDevice(&device));
+  B200_REQUIRE(device < count, "b200_ctx_create: device %d out of range (%d)", device, count);
+  B200_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  B200_CUDA(cudaGetDeviceProperties(&prop, device));
+  B200_REQUIRE(prop.major == 10, "b200_ctx_create: device %d is sm_%d%d; this build is sm_100a only",
+               device, prop.major, prop.minor);
+  b200_ctx* ctx = new b200_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->l2_bytes = (size_t)prop.l2CacheSize;
+  B200_CUDA(cudaStreamCreateWithFlags(&ctx->own_compute, cudaStreamNonBlocking));
+  ctx->compute = ctx->own_compute;
+  for (int l = 0; l < B200_NUM_LANES; l++) {
+    B200_CUDA(cudaStreamCreateWithFlags(&ctx->lane[l], cudaStreamNonBlocking));
+    B200_CUDA(cudaEventCreateWithFlags(&ctx->lane_done[l], cudaEventDisableTiming));
+  }
+  B200_CUDA(cudaEventCreateWithFlags(&ctx->compute_done, cudaEventDisableTiming));
+  B200_CUDA(cudaEventCreate(&ctx->t0));
+  B200_CUDA(cudaEventCreate(&ctx->t1));
+  ctx->num_counters = 1 << 16;
+  B200_CUDA(cudaMalloc((void**)&ctx->counters, ctx->num_counters * sizeof(unsigned int)));
+  B200_CUDA(cudaMemset(ctx->counters, 0, ctx->num_counters * sizeof(unsigned int)));
+  *out = ctx;
+  return 0;
+}
+
+int b200_ctx_destroy(b200_ctx* ctx) {
+  if (!ctx) return 0;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (auto& b : ctx->pinned_cache) cudaFreeHost(b.ptr);
+  for (auto& b : ctx->device_cache) cudaFree(b.ptr);
+  if (ctx->workspace) cudaFree(ctx->workspace);
+  if (ctx->counters) cudaFree(ctx->counters);
+  for (int l = 0; l < B200_NUM_LANES; l++) {
+    if (ctx->lane[l]) cudaStreamDestroy(ctx->lane[l]);
+    if (ctx->lane_done[l]) cudaEventDestroy(ctx->lane_done[l]);
+  }
+  if (ctx->compute_done) cudaEventDestroy(ctx->compute_done);
+  if (ctx->t0) cudaEventDestroy(ctx->t0);
+  if (ctx->t1) cudaEventDestroy(ctx->t1);
+  if (ctx->own_compute) cudaStreamDestroy(ctx->own_compute);
+  delete ctx;
+  return 0;
+}
+
+int b200_ctx_set_stream(b200_ctx* ctx, void* cuda_stream) {
+  B200_REQUIRE(ctx, "b200_ctx_set_stream: null context");
+  ctx->compute = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_compute;
+  return 0;
+}
+
+int b200_ctx_device(const b200_ctx* ctx, int* device, int* sm_count) {
+  B200_REQUIRE(ctx, "b200_ctx_device: null context");
+  if (device) *device = ctx->device;
+  if (sm_count) *sm_count = ctx->sm_count;
+  return 0;
+}
+
+int b200_alloc(b200_ctx* ctx, int mode, size_t bytes, void** host, void** dev) {
+  B200_REQUIRE(ctx && host && dev, "b200_alloc: null argument");
+  *host = *dev = nullptr;
+  if (bytes == 0) bytes = 1;
+  if (mode == B200_OFFLOAD_UNIFIED) {
+    void* p = nullptr;
+    B200_CUDA(cudaMallocManaged(&p, bytes, cudaMemAttachGlobal));
+    *host = *dev = p;
+    return 0;
+  }
+  B200_REQUIRE(mode == B200_OFFLOAD_ALWAYS || mode == B200_OFFLOAD_ONCE,
+               "b200_alloc: unknown offload mode %d", mode);
+  const size_t cap = round_capacity(bytes);
+  void* h = cache_take(ctx->pinned_cache, cap);
+  if (!h) B200_CUDA(cudaMallocHost(&h, cap));
+  void* d = cache_take(ctx->device_cache, cap);
+  if (!d) {
+    cudaError_t e = cudaMalloc(&d, cap);
+    if (e != cudaSuccess) {
+      cudaFreeHost(h);
+      set_error("b200_alloc: cudaMalloc(%zu) -> %s", cap, cudaGetErrorString(e));
+      return 1;
+    }
+  }
+  ctx->live_host.push_back({h, cap});
+  ctx->live_dev.push_back({d, cap});
+  *host = h;
+  *dev = d;
+  return 0;
+}
+
+int b200_free(b200_ctx* ctx, int mode, void* host, void* dev) {
+  B200_REQUIRE(ctx, "b200_free: null context");
+  if (mode == B200_OFFLOAD_UNIFIED) {
+    if (host) B200_CUDA(cudaFree(host));
+    return 0;
+  }
+  // cached blocks may be handed out again immediately: queued work must be done
+  if (ctx->compute_dirty || ctx->lane_dirty[0] || ctx->lane_dirty[1] || ctx->lane_dirty[2])
+    if (b200_sync(ctx)) return 1;
+  if (host) {
+    const size_t cap = live_pop(ctx->live_host, host);
+    if (cap)
+      cache_put(ctx->pinned_cache, host, cap, (size_t)6 << 30, [](void* p) { cudaFreeHost(p); });
+    else
+      B200_CUDA(cudaFreeHost(host));
+  }
+  if (dev) {
+    const size_t cap = live_pop(ctx->live_dev, dev);
+    if (cap)
+      cache_put(ctx->device_cache, dev, cap, (size_t)48 << 30, [](void* p) { cudaFree(p); });
+    else
+      B200_CUDA(cudaFree(dev));
+  }
+  return 0;
+}
+
+int b200_h2d_async(b200_ctx* ctx, void* dev, const void* host, size_t bytes, int lane) {
+  B200_REQUIRE(ctx && lane >= 0 && lane < B200_NUM_LANES, "b200_h2d_async: bad lane %d", lane);
+  if (bytes == 0) return 0;
+  if (lanes_wait_for_compute(ctx)) return 1;
+  B200_CUDA(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx->lane[lane]));
+  B200_CUDA(cudaEventRecord(ctx->lane_done[lane], ctx->lane[lane]));
+  ctx->lane_pending[lane] = true;
+  ctx->lane_dirty[lane] = true;
+  return 0;
+}
+
+int b200_d2h_async(b200_ctx* ctx, void* host, const void* dev, size_t bytes, int lane) {
+  B200_REQUIRE(ctx && lane >= 0 && lane < B200_NUM_LANES, "b200_d2h_async: bad lane %d", lane);
+  if (bytes == 0) return 0;
+  if (lanes_wait_for_compute(ctx)) return 1;
+  B200_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->lane[lane]));
+  ctx->lane_dirty[lane] = true;
+  return 0;
+}
+
+int b200_prefetch_async(b200_ctx* ctx, const void* managed, size_t bytes, int to_device, int lane) {
+  B200_REQUIRE(ctx && lane >= 0 && lane < B200_NUM_LANES, "b200_prefetch_async: bad lane %d", lane);
+  if (bytes == 0) return 0;
+  if (lanes_wait_for_compute(ctx)) return 1;
+  B200_CUDA(cudaMemPrefetchAsync(managed, bytes, to_device ? ctx->device : cudaCpuDeviceId,
+                                 ctx->lane[lane]));
+  if (to_device) {
+    B200_CUDA(cudaEventRecord(ctx->lane_done[lane], ctx->lane[lane]));
+    ctx->lane_pending[lane] = true;
+  }
+  ctx->lane_dirty[lane] = true;
+  return 0;
+}
+
+int b200_advise(b200_ctx* ctx, const void* managed, size_t bytes, int is_input) {
+  B200_REQUIRE(ctx && managed, "b200_advise: null argument");
+  if (bytes == 0) return 0;
+  B200_CUDA(cudaMemAdvise(managed, bytes, cudaMemAdviseSetPreferredLocation, ctx->device));
+  if (is_input) B200_CUDA(cudaMemAdvise(managed, bytes, cudaMemAdviseSetAccessedBy, cudaCpuDeviceId));
+  return 0;
+}
+
+int b200_sync(b200_ctx* ctx) {
+  B200_REQUIRE(ctx, "b200_sync: null context");
+  B200_CUDA(cudaStreamSynchronize(ctx->compute));
+  for (int l = 0; l < B200_NUM_LANES; l++) {
+    if (ctx->lane_dirty[l]) B200_CUDA(cudaStreamSynchronize(ctx->lane[l]));
+    ctx->lane_dirty[l] = false;
+    ctx->lane_pending[l] = false;
+  }
+  ctx->compute_dirty = false;
+  ctx->compute_unordered = false;
+  return 0;
+}
+
+// ------------------------------------------------------------------ compute
+
+static int check_gemm_args(const char* who, int ta, int tb, int m, int n, int k, const void* A,
+                           int lda, const void* B, int ldb, const void* C, int ldc) {
+  B200_REQUIRE((ta == 0 || ta == 1) && (tb == 0 || tb == 1), "%s: bad transpose flag", who);
+  B200_REQUIRE(m >= 0 && n >= 0 && k >= 0, "%s: negative dimension (m=%d n=%d k=%d)", who, m, n, k);
+  const int rowsA = ta ? k : m, rowsB = tb ? n : k;
+  B200_REQUIRE(lda >= std::max(1, rowsA), "%s: lda=%d < max(1,%d)", who, lda, rowsA);
+  B200_REQUIRE(ldb >= std::max(1, rowsB), "%s: ldb=%d < max(1,%d)", who, ldb, rowsB);
+  B200_REQUIRE(ldc >= std::max(1, m), "%s: ldc=%d < max(1,%d)", who, ldc, m);
+  if (m > 0 && n > 0)
+    B200_REQUIRE(C != nullptr && (k == 0 || (A != nullptr && B != nullptr)), "%s: null operand", who);
+  return 0;
+}
+
+int b200_dgemm(b200_ctx* ctx, int ta, int tb, int m, int n, int k, double alpha, const double* A,
+               int lda, const double* B, int ldb, double beta, double* C, int ldc) {
+  B200_REQUIRE(ctx, "b200_dgemm: null context");
+  if (int r = check_gemm_args("b200_dgemm", ta, tb, m, n, k, A, lda, B, ldb, C, ldc)) return r;
+  if (m == 0 || n == 0) return 0;
+  if (join_lanes_into_compute(ctx)) return 1;
+  if (!ta && !tb && k > 0 && alpha != 0.0) {
+    const int r = dgemm_dmma_dispatch(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+    if (r >= 0) return r;
+  }
+  return gemm_simt_dispatch<double>(ctx, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+}
+
+int b200_sgemm(b200_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha, const float* A,
+               int lda, const float* B, int ldb, float beta, float* C, int ldc) {
+  B200_REQUIRE(ctx, "b200_sgemm: null context");
+  if (int r = check_gemm_args("b200_sgemm", ta, tb, m, n, k, A, lda, B, ldb, C, ldc)) return r;
+  if (m == 0 || n == 0) return 0;
+  if (join_lanes_into_compute(ctx)) return 1;
+  if (!ta && !tb && k > 0 && alpha != 0.0f) {
+    const int r = sgemm_tc_dispatch(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+    if (r >= 0) return r;
+  }
+  return gemm_simt_dispatch<float>(ctx, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+}
+
+static int check_gemv_args(const char* who, int trans, int m, int n, const void* A, int lda,
+                           const void* x, int incx, const void* y, int incy) {
+  B200_REQUIRE(trans == 0 || trans == 1, "%s: bad transpose flag", who);
+  B200_REQUIRE(m >= 0 && n >= 0, "%s: negative dimension (m=%d n=%d)", who, m, n);
+  B200_REQUIRE(lda >= std::max(1, m), "%s: lda=%d < max(1,%d)", who, lda, m);
+  B200_REQUIRE(incx != 0 && incy != 0, "%s: zero increment", who);
+  if (m > 0 && n > 0) B200_REQUIRE(A && x && y, "%s: null operand", who);
+  return 0;
+}
+
+int b200_dgemv(b200_ctx* ctx, int trans, int m, int n, double alpha, const double* A, int lda,
+               const double* x, int incx, double beta, double* y, int incy) {
+  B200_REQUIRE(ctx, "b200_dgemv: null context");
+  if (int r = check_gemv_args("b200_dgemv", trans, m, n, A, lda, x, incx, y, incy)) return r;
+  if (join_lanes_into_compute(ctx)) return 1;
+  return gemv_dispatch<double>(ctx, trans, m, n, alpha, A, lda, x, incx, beta, y, incy);
+}
+
+int b200_sgemv(b200_ctx* ctx, int trans, int m, int n, float alpha, const float* A, int lda,
+               const float* x, int incx, float beta, float* y, int incy) {
+  B200_REQUIRE(ctx, "b200_sgemv: null context");
+  if (int r = check_gemv_args("b200_sgemv", trans, m, n, A, lda, x, incx, y, incy)) return r;
+  if (join_lanes_into_compute(ctx)) return 1;
+  return gemv_dispatch<float>(ctx, trans, m, n, alpha, A, lda, x, incx, beta, y, incy);
+}
+
+}  // extern "C"
+
+// ------------------------------------------------ Always-mode transfer engine
+
+namespace {
+
+// Number of column slabs for an operand set of `bytes`: small problems go in
+// one shot (fewest API calls), large ones are cut so copies hide behind compute.
+int pick_slabs(size_t bytes, int cols) {
+  if (bytes < ((size_t)8 << 20) || cols < 2) return 1;
+  int s = (int)std::min<size_t>(16, bytes / ((size_t)4 << 20));
+  return std::max(1, std::min(s, cols));
+}
+
+template <typename T, typename GemmFn>
+int gemm_offload(b200_ctx* ctx, int m, int n, int k, T alpha, const T* hA, T* dA, int lda,
+                 const T* hB, T* dB, int ldb, T beta, T* hC, T* dC, int ldc, GemmFn gemm) {
+  B200_REQUIRE(ctx && hA && dA && hB && dB && hC && dC, "gemm_offload: null argument");
+  B200_REQUIRE(m >= 0 && n >= 0 && k >= 0, "gemm_offload: negative dimension");
+  if (m == 0 || n == 0) return 0;
+  const size_t s = sizeof(T);
+  const size_t bytesA = s * (size_t)lda * k, bytesB = s * (size_t)ldb * n, bytesC = s * (size_t)ldc * n;
+  const int slabs = pick_slabs(bytesA + bytesB + bytesC, n);
+  const int cols = (n + slabs - 1) / slabs;
+  // A is needed by every slab: lane 0.  (C is only uploaded when beta != 0 --
+  // with beta == 0 BLAS never reads it, so the reference's third upload,
+  // cuBLAS/gemm.hh:130-131, is dead traffic.)
+  if (b200_h2d_async(ctx, dA, hA, bytesA, 0)) return 1;
+  for (int j0 = 0; j0 < n; j0 += cols) {
+    const int nc = std::min(cols, n - j0);
+    if (b200_h2d_async(ctx, dB + (size_t)j0 * ldb, hB + (size_t)j0 * ldb, s * (size_t)ldb * nc, 1)) return 1;
+    if (beta != T(0))
+      if (b200_h2d_async(ctx, dC + (size_t)j0 * ldc, hC + (size_t)j0 * ldc, s * (size_t)ldc * nc, 1)) return 1;
+    if (gemm(ctx, 0, 0, m, nc, k, alpha, dA, lda, dB + (size_t)j0 * ldb, ldb, beta,
+             dC + (size_t)j0 * ldc, ldc))
+      return 1;
+    if (b200_d2h_async(ctx, hC + (size_t)j0 * ldc, dC + (size_t)j0 * ldc, s * (size_t)ldc * nc, 2)) return 1;
+  }
+  return b200_sync(ctx);
+}
+
+template <typename T, typename GemvFn>
+int gemv_offload(b200_ctx* ctx, int m, int n, T alpha, const T* hA, T* dA, int lda, const T* hx,
+                 T* dx, T beta, T* hy, T* dy, GemvFn gemv) {
+  B200_REQUIRE(ctx && hA && dA && hx && dx && hy && dy, "gemv_offload: null argument");
+  B200_REQUIRE(m >= 0 && n >= 0, "gemv_offload: negative dimension");
+  if (m == 0) return 0;
+  const size_t s = sizeof(T);
+  const int slabs = pick_slabs(s * (size_t)lda * n, n);
+  const int cols = (n + slabs - 1) / slabs;
+  if (b200_h2d_async(ctx, dx, hx, s * (size_t)n, 1)) return 1;
+  if (beta != T(0))
+    if (b200_h2d_async(ctx, dy, hy, s * (size_t)m, 1)) return 1;
+  // y accumulates over column slabs: slab j computes while slab j+1 uploads
+  if (n == 0) {
+    if (gemv(ctx, 0, m, 0, alpha, dA, lda, dx, 1, beta, dy, 1)) return 1;
+  }
+  for (int j0 = 0, i = 0; j0 < n; j0 += cols, i++) {
+    const int nc = std::min(cols, n - j0);
+    if (b200_h2d_async(ctx, dA + (size_t)j0 * lda, hA + (size_t)j0 * lda, s * (size_t)lda * nc,
+                       (i & 1) ? 2 : 0))
+      return 1;
+    if (gemv(ctx, 0, m, nc, alpha, dA + (size_t)j0 * lda, lda, dx + j0, 1, i == 0 ? beta : T(1), dy, 1))
+      return 1;
+  }
+  if (b200_d2h_async(ctx, hy, dy, s * (size_t)m, 2)) return 1;
+  return b200_sync(ctx);
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200_dgemm_offload(b200_ctx* ctx, int m, int n, int k, double alpha, const double* hA, double* dA,
+                       int lda, const double* hB, double* dB, int ldb, double beta, double* hC,
+                       double* dC, int ldc) {
+  return gemm_offload<double>(ctx, m, n, k, alpha, hA, dA, lda, hB, dB, ldb, beta, hC, dC, ldc, b200_dgemm);
+}
+int b200_sgemm_offload(b200_ctx* ctx, int m, int n, int k, float alpha, const float* hA, float* dA,
+                       int lda, const float* hB, float* dB, int ldb, float beta, float* hC, float* dC,
+                       int ldc) {
+  return gemm_offload<float>(ctx, m, n, k, alpha, hA, dA, lda, hB, dB, ldb, beta, hC, dC, ldc, b200_sgemm);
+}
+int b200_dgemv_offload(b200_ctx* ctx, int m, int n, double alpha, const double* hA, double* dA, int lda,
+                       const double* hx, double* dx, double beta, double* hy, double* dy) {
+  return gemv_offload<double>(ctx, m, n, alpha, hA, dA, lda, hx, dx, beta, hy, dy, b200_dgemv);
+}
+int b200_sgemv_offload(b200_ctx* ctx, int m, int n, float alpha, const float* hA, float* dA, int lda,
+                       const float* hx, float* dx, float beta, float* hy, float* dy) {
+  return gemv_offload<float>(ctx, m, n, alpha, hA, dA, lda, hx, dx, beta, hy, dy, b200_sgemv);
+}
+
+// ------------------------------------------------------------ introspection
+
+const char* b200_last_kernel(const b200_ctx* ctx) { return ctx ? ctx->last_kernel : "none"; }
+unsigned long long b200_launch_count(const b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int b200_timer_start(b200_ctx* ctx) {
+  B200_REQUIRE(ctx, "b200_timer_start: null context");
+  B200_CUDA(cudaEventRecord(ctx->t0, ctx->compute));
+  return 0;
+}
+int b200_timer_stop(b200_ctx* ctx, float* ms) {
+  B200_REQUIRE(ctx && ms, "b200_timer_stop: null argument");
+  B200_CUDA(cudaEventRecord(ctx->t1, ctx->compute));
+  B200_CUDA(cudaEventSynchronize(ctx->t1));
+  B200_CUDA(cudaEventElapsedTime(ms, ctx->t0, ctx->t1));
+  return 0;
+}
+
+int b200_probe_peak(b200_ctx* ctx, const char* which, double* result) {
+  B200_REQUIRE(ctx, "b200_probe_peak: null context");
+  return probe_peak(ctx, which, result);
+}
+
+}  // extern "C"

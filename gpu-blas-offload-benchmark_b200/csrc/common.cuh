@@ -1,0 +1,118 @@
+// common.cuh -- context, error plumbing and small device helpers shared by the
+// translation units of libb200blas.so.  sm_100a only.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <vector>
+
+#include "../../include/b200blas.h"
+
+namespace b200 {
+
+void set_error(const char* fmt, ...);
+
+#define B200_CUDA(call)                                                        \
+  do {                                                                         \
+    cudaError_t e__ = (call);                                                  \
+    if (e__ != cudaSuccess) {                                                  \
+      b200::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call,            \
+                      cudaGetErrorString(e__));                                \
+      return 1;                                                                \
+    }                                                                          \
+  } while (0)
+
+#define B200_REQUIRE(cond, ...)                                                \
+  do {                                                                         \
+    if (!(cond)) {                                                             \
+      b200::set_error(__VA_ARGS__);                                            \
+      return 2;                                                                \
+    }                                                                          \
+  } while (0)
+
+struct CachedBlock {
+  void* ptr;
+  size_t capacity;
+};
+
+}  // namespace b200
+
+// The opaque context of the C ABI.
+struct b200_ctx {
+  int device = 0;
+  int sm_count = 148;
+  size_t l2_bytes = 0;
+  cudaStream_t own_compute = nullptr;  // non-blocking
+  cudaStream_t compute = nullptr;      // own_compute or a caller stream
+  cudaStream_t lane[B200_NUM_LANES] = {};
+  cudaEvent_t lane_done[B200_NUM_LANES] = {};
+  bool lane_pending[B200_NUM_LANES] = {};  // compute must wait for this lane
+  bool lane_dirty[B200_NUM_LANES] = {};    // lane has un-synchronised work
+  cudaEvent_t compute_done = nullptr;
+  bool compute_dirty = false;      // kernels issued since the last b200_sync
+  bool compute_unordered = false;  // kernels issued since compute_done was recorded
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+
+  // scratch: split-K / split-N partials, 3xTF32 operand splits
+  void* workspace = nullptr;
+  size_t workspace_bytes = 0;
+  // self-resetting arrival counters for last-block reductions
+  unsigned int* counters = nullptr;
+  int num_counters = 0;
+
+  std::vector<b200::CachedBlock> pinned_cache, device_cache;  // freed, reusable
+  std::vector<b200::CachedBlock> live_host, live_dev;         // handed out
+
+  const char* last_kernel = "none";
+  unsigned long long launches = 0;
+};
+
+namespace b200 {
+
+int ensure_workspace(b200_ctx* ctx, size_t bytes);
+// Make the compute stream wait for every copy lane that has pending uploads.
+int join_lanes_into_compute(b200_ctx* ctx);
+inline void note_launch(b200_ctx* ctx, const char* name, int n = 1) {
+  ctx->last_kernel = name;
+  ctx->launches += (unsigned long long)n;
+  ctx->compute_dirty = true;
+  ctx->compute_unordered = true;
+}
+
+// ---- kernel-family entry points (one per .cu) -----------------------------
+template <typename T>
+int gemv_dispatch(b200_ctx* ctx, int trans, int m, int n, T alpha, const T* A,
+                  int lda, const T* x, int incx, T beta, T* y, int incy);
+
+template <typename T>
+int gemm_simt_dispatch(b200_ctx* ctx, int ta, int tb, int m, int n, int k,
+                       T alpha, const T* A, int lda, const T* B, int ldb, T beta,
+                       T* C, int ldc);
+
+// FP64 tensor-core (DMMA) path; returns -1 if the shape is not eligible.
+int dgemm_dmma_dispatch(b200_ctx* ctx, int m, int n, int k, double alpha,
+                        const double* A, int lda, const double* B, int ldb,
+                        double beta, double* C, int ldc);
+
+// 3xTF32 tcgen05/TMEM path; returns -1 if the shape is not eligible.
+int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha,
+                      const float* A, int lda, const float* B, int ldb,
+                      float beta, float* C, int ldc);
+
+int probe_peak(b200_ctx* ctx, const char* which, double* result);
+
+// ---- device helpers --------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace b200

@@ -1,0 +1,274 @@
+// dgemm_dmma.cu -- DGEMM on the FP64 tensor-core pipe (DMMA) for sm_100a.
+//
+// Replaces cublasGemmEx(..., CUDA_R_64F, ..., CUBLAS_COMPUTE_64F, ...) at
+// reference cuBLAS/gemm.hh:141-146,165-170,183-187 for column-major
+// NoTrans/NoTrans operands (the only form the harness issues).
+//
+// FP64 has no tcgen05/TMEM path on Blackwell; the FP64 tensor instruction is
+// warp-level mma.sync m8n8k4 (SASS DMMA.8x8x4).  Structure:
+//   * CTA tile 128x128x16, 8 warps as 2(M) x 4(N), warp tile 64x32 = 8x4 DMMA
+//     tiles -> 64 accumulator doubles per thread, 12 fragment loads per 32 DMMA.
+//   * 4-stage cp.async pipeline (16-byte copies when lda/ldb/pointers allow,
+//     8-byte otherwise), zero-filled at the ragged edges via src-size, so any
+//     m, n, k works without a separate edge kernel.
+//   * A stage is [k][m] with row stride 132 doubles, B stage is [n][k] with row
+//     stride 20 doubles: both strides are 8 words mod 32 banks, which makes
+//     every fragment LDS.64 of a half-warp (4 k x 4 m|n) conflict-free, and the
+//     global->smem copies keep the operands' native column-major order (A is
+//     M-contiguous, B is K-contiguous) -- no transposition anywhere.
+//   * grouped tile order (8 tile-rows per group) so co-resident CTAs share A/B
+//     panels in the 126 MB L2.
+//   * split-K with workspace + last-arriving-CTA reduction when the tile count
+//     cannot fill 148 SMs.
+#include "common.cuh"
+
+namespace b200 {
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16;
+constexpr int STAGES = 4;
+constexpr int NTHREADS = 256;
+constexpr int A_LD = BM + 4;  // doubles; 132*2 words = 8 mod 32
+constexpr int B_LD = BK + 4;  // doubles; 20*2 words  = 8 mod 32
+constexpr int A_STAGE = BK * A_LD;  // doubles
+constexpr int B_STAGE = BN * B_LD;
+constexpr size_t SMEM_BYTES = (size_t)STAGES * (A_STAGE + B_STAGE) * sizeof(double);
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* g, int src_bytes) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(g), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* g, int src_bytes) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(g), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile(
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
+}
+
+template <bool ALIGNED>
+__global__ void __launch_bounds__(NTHREADS, 1)
+dgemm_dmma_kernel(int m, int n, int k, double alpha, const double* __restrict__ A,
+                  long long lda, const double* __restrict__ B, long long ldb,
+                  double beta, double* __restrict__ C, long long ldc, int tiles_m,
+                  int tiles_n, int k_per_split, double* __restrict__ partial,
+                  unsigned int* __restrict__ counters) {
+  extern __shared__ __align__(16) double smem[];
+  double* As = smem;                      // [STAGES][BK][A_LD]
+  double* Bs = smem + STAGES * A_STAGE;   // [STAGES][BN][B_LD]
+  __shared__ bool is_last;
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int wm = warp & 1, wn = warp >> 1;  // 2 x 4 warps
+  const int g = lane >> 2, t = lane & 3;
+
+  // grouped rasterisation
+  constexpr int GROUP = 8;
+  const int bid = blockIdx.x;
+  const int group_size = GROUP * tiles_n;
+  const int first_m = (bid / group_size) * GROUP;
+  const int gm = min(tiles_m - first_m, GROUP);
+  const int tm = first_m + (bid % group_size) % gm;
+  const int tn = (bid % group_size) / gm;
+  const int m0 = tm * BM, n0 = tn * BN;
+
+  const int kbeg = blockIdx.y * k_per_split;
+  const int kend = min(k, kbeg + k_per_split);
+  const int ntiles = (kend - kbeg + BK - 1) / BK;
+
+  auto load_tile = [&](int kt, int stage) {
+    const int kb = kbeg + kt * BK;
+    double* as = As + stage * A_STAGE;
+    double* bs = Bs + stage * B_STAGE;
+    if (ALIGNED) {
+      // A: BK columns x 64 16-byte chunks
+#pragma unroll
+      for (int l = 0; l < (BK * BM / 2) / NTHREADS; l++) {
+        const int e = tid + l * NTHREADS;
+        const int c = e % (BM / 2), p = e / (BM / 2);
+        const int gi = m0 + 2 * c, gp = kb + p;
+        int bytes = 0;
+        if (gp < kend) bytes = max(0, min(2, m - gi)) * 8;
+        const double* src = bytes ? A + gi + gp * lda : A;
+        cp_async16(as + p * A_LD + 2 * c, src, bytes);
+      }
+      // B: BN columns x 8 16-byte chunks along k
+#pragma unroll
+      for (int l = 0; l < (BN * BK / 2) / NTHREADS; l++) {
+        const int e = tid + l * NTHREADS;
+        const int c = e % (BK / 2), j = e / (BK / 2);
+        const int gp = kb + 2 * c, gj = n0 + j;
+        int bytes = 0;
+        if (gj < n) bytes = max(0, min(2, kend - gp)) * 8;
+        const double* src = bytes ? B + gp + gj * ldb : B;
+        cp_async16(bs + j * B_LD + 2 * c, src, bytes);
+      }
+    } else {
+#pragma unroll
+      for (int l = 0; l < (BK * BM) / NTHREADS; l++) {
+        const int e = tid + l * NTHREADS;
+        const int i = e % BM, p = e / BM;
+        const int gi = m0 + i, gp = kb + p;
+        const bool ok = gi < m && gp < kend;
+        cp_async8(as + p * A_LD + i, ok ? A + gi + gp * lda : A, ok ? 8 : 0);
+      }
+#pragma unroll
+      for (int l = 0; l < (BN * BK) / NTHREADS; l++) {
+        const int e = tid + l * NTHREADS;
+        const int p = e % BK, j = e / BK;
+        const int gp = kb + p, gj = n0 + j;
+        const bool ok = gj < n && gp < kend;
+        cp_async8(bs + j * B_LD + p, ok ? B + gp + gj * ldb : B, ok ? 8 : 0);
+      }
+    }
+  };
+
+  double acc[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; s++) {
+    if (s < ntiles) load_tile(s, s);
+    cp_async_commit();
+  }
+
+  for (int kt = 0; kt < ntiles; kt++) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {
+      const int nk = kt + STAGES - 1;
+      if (nk < ntiles) load_tile(nk, nk % STAGES);
+      cp_async_commit();
+    }
+    const double* as = As + (kt % STAGES) * A_STAGE + wm * 64 + g;
+    const double* bs = Bs + (kt % STAGES) * B_STAGE + (wn * 32 + g) * B_LD;
+#pragma unroll
+    for (int k4 = 0; k4 < BK / 4; k4++) {
+      double a[8], b[4];
+#pragma unroll
+      for (int mi = 0; mi < 8; mi++) a[mi] = as[(k4 * 4 + t) * A_LD + mi * 8];
+#pragma unroll
+      for (int ni = 0; ni < 4; ni++) b[ni] = bs[ni * 8 * B_LD + k4 * 4 + t];
+#pragma unroll
+      for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+    }
+  }
+  cp_async_wait<0>();
+
+  if (gridDim.y > 1) {
+    // split-K: every CTA publishes its fragment-ordered partial tile
+    const long long tile_elems = (long long)BM * BN;
+    const long long zstride = (long long)gridDim.x * tile_elems;
+    double* mine = partial + (long long)blockIdx.y * zstride + (long long)bid * tile_elems;
+#pragma unroll
+    for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+      for (int ni = 0; ni < 4; ni++)
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+          mine[((mi * 4 + ni) * 2 + r) * NTHREADS + tid] = acc[mi][ni][r];
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned int prev = atomicAdd(&counters[bid], 1u);
+      is_last = (prev == gridDim.y - 1);
+      if (is_last) counters[bid] = 0;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const double* base = partial + (long long)bid * tile_elems;
+#pragma unroll
+    for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+      for (int ni = 0; ni < 4; ni++)
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+          double s = 0.0;
+          for (int z = 0; z < (int)gridDim.y; z++)
+            s += __ldcg(base + z * zstride + ((mi * 4 + ni) * 2 + r) * NTHREADS + tid);
+          acc[mi][ni][r] = s;
+        }
+  }
+
+  // epilogue: each accumulator register covers 8 consecutive rows x 4 columns
+#pragma unroll
+  for (int ni = 0; ni < 4; ni++) {
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      const int gj = n0 + wn * 32 + ni * 8 + t * 2 + r;
+      if (gj >= n) continue;
+#pragma unroll
+      for (int mi = 0; mi < 8; mi++) {
+        const int gi = m0 + wm * 64 + mi * 8 + g;
+        if (gi >= m) continue;
+        double* cp = C + gi + gj * ldc;
+        const double v = alpha * acc[mi][ni][r];
+        *cp = (beta == 0.0) ? v : v + beta * *cp;
+      }
+    }
+  }
+}
+
+bool g_attr_set[2] = {false, false};
+
+}  // namespace
+
+int dgemm_dmma_dispatch(b200_ctx* ctx, int m, int n, int k, double alpha,
+                        const double* A, int lda, const double* B, int ldb,
+                        double beta, double* C, int ldc) {
+  if (m < 64 || n < 64 || k < 16) return -1;  // sub-tile problems: SIMT path
+  const int tiles_m = (m + BM - 1) / BM, tiles_n = (n + BN - 1) / BN;
+  const long long tiles = (long long)tiles_m * tiles_n;
+  if (tiles > 0x7fffffffLL) return -1;
+  const bool aligned = (lda % 2 == 0) && (ldb % 2 == 0) &&
+                       ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0);
+  int splits = 1;
+  if (tiles < ctx->sm_count && tiles <= ctx->num_counters) {
+    splits = (int)((ctx->sm_count + tiles - 1) / tiles);
+    const int max_splits = k / (BK * 8);
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+  }
+  int k_per_split = ((k + splits - 1) / splits + BK - 1) / BK * BK;
+  splits = (k + k_per_split - 1) / k_per_split;
+  double* partial = nullptr;
+  if (splits > 1) {
+    if (ensure_workspace(ctx, (size_t)splits * tiles * BM * BN * sizeof(double))) return 1;
+    partial = (double*)ctx->workspace;
+  }
+  if (splits > 65535) return -1;
+  auto kern = aligned ? dgemm_dmma_kernel<true> : dgemm_dmma_kernel<false>;
+  if (!g_attr_set[aligned]) {
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)SMEM_BYTES));
+    g_attr_set[aligned] = true;
+  }
+  dim3 grid((unsigned)tiles, splits);
+  kern<<<grid, NTHREADS, SMEM_BYTES, ctx->compute>>>(
+      m, n, k, alpha, A, (long long)lda, B, (long long)ldb, beta, C, (long long)ldc,
+      tiles_m, tiles_n, k_per_split, partial, ctx->counters);
+  B200_CUDA(cudaGetLastError());
+  note_launch(ctx, aligned ? (splits > 1 ? "dgemm_dmma_128x128x16_cp16_splitk"
+                                         : "dgemm_dmma_128x128x16_cp16")
+                           : (splits > 1 ? "dgemm_dmma_128x128x16_cp8_splitk"
+                                         : "dgemm_dmma_128x128x16_cp8"));
+  return 0;
+}
+
+}  // namespace b200
