@@ -12,6 +12,7 @@
 //   download on lane L -> lane waits on an event recorded after the last kernel
 // so back-to-back kernels in Once mode cost one launch each and nothing else.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -122,6 +123,12 @@ const char* b200_version(void) { return "b200blas 0.1 (sm_100a)"; }
 int b200_ctx_create(b200_ctx** out, int device) {
   B200_REQUIRE(out != nullptr, "b200_ctx_create: out is null");
   *out = nullptr;
+  // Load every kernel of this library when the CUDA context is created instead
+  // of on first launch: a lazily loaded kernel would otherwise be charged to
+  // whichever timed region happens to launch it first.  Only effective when
+  // this call is the one that initialises CUDA (it is, in the harness); an
+  // explicit user setting wins.
+  setenv("CUDA_MODULE_LOADING", "EAGER", 0);
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count == 0) {

@@ -6,13 +6,13 @@
 //
 // FP64 has no tcgen05/TMEM path on Blackwell; the FP64 tensor instruction is
 // warp-level mma.sync m8n8k4 (SASS DMMA.8x8x4).  Structure:
-//   * CTA tile 128x128x16, 8 warps as 2(M) x 4(N), warp tile 64x32 = 8x4 DMMA
+//   * CTA tile 128x128x32, 8 warps as 2(M) x 4(N), warp tile 64x32 = 8x4 DMMA
 //     tiles -> 64 accumulator doubles per thread, 12 fragment loads per 32 DMMA.
-//   * 4-stage cp.async pipeline (16-byte copies when lda/ldb/pointers allow,
+//   * 3-stage cp.async pipeline (16-byte copies when lda/ldb/pointers allow,
 //     8-byte otherwise), zero-filled at the ragged edges via src-size, so any
 //     m, n, k works without a separate edge kernel.
 //   * A stage is [k][m] with row stride 132 doubles, B stage is [n][k] with row
-//     stride 20 doubles: both strides are 8 words mod 32 banks, which makes
+//     stride 36 doubles: both strides are 8 words mod 32 banks, which makes
 //     every fragment LDS.64 of a half-warp (4 k x 4 m|n) conflict-free, and the
 //     global->smem copies keep the operands' native column-major order (A is
 //     M-contiguous, B is K-contiguous) -- no transposition anywhere.
@@ -25,14 +25,15 @@
 namespace b200 {
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 16;
-constexpr int STAGES = 4;
+constexpr int BM = 128, BN = 128, BK = 32;
+constexpr int STAGES = 3;
 constexpr int NTHREADS = 256;
 constexpr int A_LD = BM + 4;  // doubles; 132*2 words = 8 mod 32
-constexpr int B_LD = BK + 4;  // doubles; 20*2 words  = 8 mod 32
+constexpr int B_LD = BK + 4;  // doubles; 36*2 words  = 8 mod 32
 constexpr int A_STAGE = BK * A_LD;  // doubles
 constexpr int B_STAGE = BN * B_LD;
 constexpr size_t SMEM_BYTES = (size_t)STAGES * (A_STAGE + B_STAGE) * sizeof(double);
+static_assert(SMEM_BYTES <= 227 * 1024, "smem budget");
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* g, int src_bytes) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -86,32 +87,54 @@ dgemm_dmma_kernel(int m, int n, int k, double alpha, const double* __restrict__ 
   const int kend = min(k, kbeg + k_per_split);
   const int ntiles = (kend - kbeg + BK - 1) / BK;
 
+  // ---- global -> shared copy plan (loop-invariant part hoisted) --------------
+  // ALIGNED: thread owns one 16-byte column chunk of A (rows 2c, 2c+1) for k-rows
+  // p0, p0+4, ... and one 16-byte k-chunk of B (k = 2cb, 2cb+1) for columns
+  // j0, j0+16, ...; per k-tile only the base pointers advance.
+  constexpr int A_CHUNKS = (BK * BM / 2) / NTHREADS;  // per thread per tile
+  constexpr int B_CHUNKS = (BN * BK / 2) / NTHREADS;
+  const int a_c = tid % (BM / 2), a_p0 = tid / (BM / 2);      // a_p0 in [0,4)
+  const int b_c = tid % (BK / 2), b_j0 = tid / (BK / 2);      // b_j0 in [0,16)
+  constexpr int A_PSTEP = NTHREADS / (BM / 2);                 // 4
+  constexpr int B_JSTEP = NTHREADS / (BK / 2);                 // 16
+  const int a_bytes = max(0, min(2, m - (m0 + 2 * a_c))) * 8;  // m-edge, invariant
+  unsigned b_mask = 0;                                         // n-edge, invariant
+#pragma unroll
+  for (int l = 0; l < B_CHUNKS; l++)
+    if (n0 + b_j0 + l * B_JSTEP < n) b_mask |= 1u << l;
+  const double* a_src = A + (m0 + 2 * a_c) + (long long)(kbeg + a_p0) * lda;
+  const double* b_src = B + (kbeg + 2 * b_c) + (long long)(n0 + b_j0) * ldb;
+  const int a_dst = a_p0 * A_LD + 2 * a_c;
+  const int b_dst = b_j0 * B_LD + 2 * b_c;
+
   auto load_tile = [&](int kt, int stage) {
     const int kb = kbeg + kt * BK;
     double* as = As + stage * A_STAGE;
     double* bs = Bs + stage * B_STAGE;
     if (ALIGNED) {
-      // A: BK columns x 64 16-byte chunks
+      const bool full_k = kb + BK <= kend;
+      const double* ap = a_src + (long long)kt * BK * lda;
+      const double* bp = b_src + kt * BK;
+      if (full_k) {
 #pragma unroll
-      for (int l = 0; l < (BK * BM / 2) / NTHREADS; l++) {
-        const int e = tid + l * NTHREADS;
-        const int c = e % (BM / 2), p = e / (BM / 2);
-        const int gi = m0 + 2 * c, gp = kb + p;
-        int bytes = 0;
-        if (gp < kend) bytes = max(0, min(2, m - gi)) * 8;
-        const double* src = bytes ? A + gi + gp * lda : A;
-        cp_async16(as + p * A_LD + 2 * c, src, bytes);
-      }
-      // B: BN columns x 8 16-byte chunks along k
+        for (int l = 0; l < A_CHUNKS; l++)
+          cp_async16(as + a_dst + l * A_PSTEP * A_LD, a_bytes ? ap + (long long)l * A_PSTEP * lda : A, a_bytes);
 #pragma unroll
-      for (int l = 0; l < (BN * BK / 2) / NTHREADS; l++) {
-        const int e = tid + l * NTHREADS;
-        const int c = e % (BK / 2), j = e / (BK / 2);
-        const int gp = kb + 2 * c, gj = n0 + j;
-        int bytes = 0;
-        if (gj < n) bytes = max(0, min(2, kend - gp)) * 8;
-        const double* src = bytes ? B + gp + gj * ldb : B;
-        cp_async16(bs + j * B_LD + 2 * c, src, bytes);
+        for (int l = 0; l < B_CHUNKS; l++) {
+          const int bytes = (b_mask >> l) & 1 ? 16 : 0;
+          cp_async16(bs + b_dst + l * B_JSTEP * B_LD, bytes ? bp + (long long)l * B_JSTEP * ldb : B, bytes);
+        }
+      } else {
+#pragma unroll
+        for (int l = 0; l < A_CHUNKS; l++) {
+          const int bytes = (kb + a_p0 + l * A_PSTEP < kend) ? a_bytes : 0;
+          cp_async16(as + a_dst + l * A_PSTEP * A_LD, bytes ? ap + (long long)l * A_PSTEP * lda : A, bytes);
+        }
+#pragma unroll
+        for (int l = 0; l < B_CHUNKS; l++) {
+          int bytes = (b_mask >> l) & 1 ? max(0, min(2, kend - (kb + 2 * b_c))) * 8 : 0;
+          cp_async16(bs + b_dst + l * B_JSTEP * B_LD, bytes ? bp + (long long)l * B_JSTEP * ldb : B, bytes);
+        }
       }
     } else {
 #pragma unroll
@@ -264,10 +287,10 @@ int dgemm_dmma_dispatch(b200_ctx* ctx, int m, int n, int k, double alpha,
       m, n, k, alpha, A, (long long)lda, B, (long long)ldb, beta, C, (long long)ldc,
       tiles_m, tiles_n, k_per_split, partial, ctx->counters);
   B200_CUDA(cudaGetLastError());
-  note_launch(ctx, aligned ? (splits > 1 ? "dgemm_dmma_128x128x16_cp16_splitk"
-                                         : "dgemm_dmma_128x128x16_cp16")
-                           : (splits > 1 ? "dgemm_dmma_128x128x16_cp8_splitk"
-                                         : "dgemm_dmma_128x128x16_cp8"));
+  note_launch(ctx, aligned ? (splits > 1 ? "dgemm_dmma_128x128x32_cp16_splitk"
+                                         : "dgemm_dmma_128x128x32_cp16")
+                           : (splits > 1 ? "dgemm_dmma_128x128x32_cp8_splitk"
+                                         : "dgemm_dmma_128x128x32_cp8"));
   return 0;
 }
 

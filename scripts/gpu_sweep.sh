@@ -11,7 +11,7 @@ CUBLAS=$PWD/oracle/_ref/gpu-blob-cublas
 cd $OUT
 for impl in cublas b200; do
   BIN=$CUBLAS; [ $impl = b200 ] && BIN=$B200
-  /usr/bin/time -f "$impl dense %es" timeout 1200 $BIN -i 10 -s 1 -d $DENSE -o $OUT/${impl}_dense > $OUT/${impl}_dense.log 2>&1
+  timeout 1200 $BIN -i 10 -s 1 -d $DENSE -o $OUT/${impl}_dense > $OUT/${impl}_dense.log 2>&1
   echo "$impl dense rc=$?"
   for d in $POINTS; do
     timeout 900 $BIN -i 10 -s $d -d $d -o $OUT/${impl}_d$d > $OUT/${impl}_d$d.log 2>&1

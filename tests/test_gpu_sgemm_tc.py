@@ -1,0 +1,59 @@
+"""The tcgen05 / TMEM 3xTF32 SGEMM path: parity with the oracle at the FP32 bar
+(<= 1e-5 element-wise), including ragged tiles (TMA zero fill), long K (FP32
+accumulation in TMEM) and beta != 0, and proof that the tensor-core kernel is
+the one that ran."""
+import numpy as np
+import pytest
+
+from oracle_lib import max_rel_err
+from test_gpu_parity import run_gemm
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [
+    (128, 128, 256), (256, 256, 256), (384, 512, 96), (640, 384, 1000), (1024, 1024, 64),
+    (260, 132, 200), (1028, 516, 260), (2048, 2048, 32), (512, 64, 4096), (64, 512, 4100),
+    (128, 128, 8192), (256, 256, 32768), (4096, 64, 4096), (1024, 1024, 1024), (2052, 1028, 516),
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_sgemm_tensor_core_path(blob, ctx, oracle, shape):
+    m, n, k = shape
+    A, B, _ = oracle.init_gemm("f32", m, n, k)
+    want = oracle.harness_gemm("f32", m, n, k)
+    got, kern = run_gemm(blob, ctx, "f32", "once", m, n, k, A, B, iters=2)
+    assert "tcgen05" in kern, kern
+    err = max_rel_err(got, want)
+    assert err <= 1e-5, (shape, kern, err)
+
+
+def test_sgemm_tensor_core_alpha_beta(blob, ctx, oracle):
+    rng = np.random.default_rng(3)
+    m, n, k = 300, 260, 128
+    lda, ldb, ldc = 304, 128, 301
+    A = rng.random(lda * k).astype(np.float32)
+    B = rng.random(ldb * n).astype(np.float32)
+    C0 = rng.random(ldc * n).astype(np.float32)
+    want = C0.copy()
+    oracle.gemm("f32", m, n, k, 1.5, A, lda, B, ldb, 0.5, want, ldc)
+    got, kern = run_gemm(blob, ctx, "f32", "once", m, n, k, A, B, C0=C0, alpha=1.5, beta=0.5,
+                         lda=lda, ldb=ldb, ldc=ldc)
+    assert "tcgen05" in kern, kern
+    assert max_rel_err(got, want) <= 1e-5
+
+
+def test_sgemm_signed_inputs_absolute_error(blob, ctx, oracle):
+    """With cancellation the relative bar is meaningless; the 3xTF32 absolute error
+    must stay at FP32 level relative to |A||B|."""
+    rng = np.random.default_rng(9)
+    m = n = k = 512
+    A = (rng.random(m * k) - 0.5).astype(np.float32)
+    B = (rng.random(k * n) - 0.5).astype(np.float32)
+    want = np.zeros(m * n, np.float32)
+    oracle.gemm("f32", m, n, k, 1.0, A, m, B, k, 0.0, want, m)
+    bound = np.zeros(m * n, np.float32)
+    oracle.gemm("f32", m, n, k, 1.0, np.abs(A), m, np.abs(B), k, 0.0, bound, m)
+    got, kern = run_gemm(blob, ctx, "f32", "once", m, n, k, A, B)
+    assert "tcgen05" in kern, kern
+    assert float(np.max(np.abs(got.astype(np.float64) - want) / bound)) <= 1e-5
