@@ -13,15 +13,19 @@
 // zero, so the tensor core's own truncation is the identity on it) and
 // lo = x - hi (exact in FP32), and the product is formed as
 //     A*B ~= A_lo*B_hi + A_hi*B_lo + A_hi*B_hi          (3 tensor-core MMAs)
-// with FP32 accumulation in TMEM; the dropped lo*lo term and the truncation of
-// lo to 11 bits are each <= 2^-21 relative.  Measured max element-wise error vs
-// the FP64-accumulating oracle is ~1e-6 at K = 8192 (bar: 1e-5).
+// the dropped lo*lo term and the truncation of lo to 11 bits are each <= 2^-21
+// relative.  The tensor core's FP32 accumulate truncates (measured bias ~7e-8
+// per K=8 step), so TMEM accumulates only 128 of K at a time and the epilogue
+// warps sum those chunks in round-to-nearest FP32 registers (bar: 1e-5).
 //
 // Layout.  Column-major operands map onto UMMA without any transposition:
 //   A (M x K, M contiguous)  = "MN-major" A: TMA boxes of {32 m, 32 k} land as
-//       [k][32 m] rows of 128 bytes, 4 such chunks per 128-row tile
-//       (descriptor: SWIZZLE_128B, LBO = 4096 between m-chunks, SBO = 1024
-//       between groups of 8 k; one K=8 MMA = one 1024-byte swizzle atom)
+//       [k][32 m] rows of 128 bytes, 4 such chunks per 128-row tile.  UMMA
+//       accepts exactly one layout for MN-major TF32: SWIZZLE_128B_BASE32B
+//       (32-byte chunks XORed with k mod 4; TMA's SWIZZLE_128B_ATOM_32B), so
+//       the descriptor is LBO = 4096 between m-chunks, SBO = 512 between groups
+//       of 4 k, start += 1024 per K=8 MMA.  (Probed on hardware with
+//       tests/cuda/tc_probe.cu: the plain SWIZZLE_128B descriptor yields zeros.)
 //   B (K x N, K contiguous)  = "K-major" B: one TMA box {32 k, 128 n} lands as
 //       [n][32 k] rows of 128 bytes (SWIZZLE_128B, SBO = 1024 between groups of
 //       8 n; successive K=8 MMAs advance the start address by 32 bytes)
@@ -49,6 +53,7 @@ constexpr int BM = 128, BN = 128, BK = 32;
 constexpr int STAGES = 3;
 constexpr int ACC_STAGES = 2;
 constexpr int UMMA_K = 8;
+constexpr int KB_PER_CHUNK = 4;  // k-blocks accumulated in TMEM before promotion (K = 128)
 constexpr int NUM_THREADS = 256;
 constexpr uint32_t TMEM_COLS = ACC_STAGES * BN;  // 256 (power of two >= 32)
 constexpr uint32_t A_TILE = BM * BK * 4;         // 16 KB: 4 chunks x [32 k][128 B]
@@ -132,11 +137,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 }
 
 // UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout):
-//   [0,14) start>>4  [16,30) LBO>>4  [32,46) SBO>>4  [46,48) version=1  [61,64) layout (2 = SWIZZLE_128B)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+//   [0,14) start>>4  [16,30) LBO>>4  [32,46) SBO>>4  [46,48) version=1  [61,64) layout type
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
-         ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+         ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46) | ((uint64_t)layout << 61);
 }
+constexpr uint32_t kSwizzle128B = 2;         // B: K-major, 16-byte swizzle atoms
+constexpr uint32_t kSwizzle128B_Base32B = 1; // A: the only layout UMMA accepts for MN-major TF32
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32,
 // A MN-major (bit 15), B K-major, N>>3 at [17,23), M>>4 at [24,29).
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (0u << 16) |
@@ -243,35 +250,43 @@ sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    // The tensor core truncates when it adds into the FP32 accumulator (measured:
+    // ~7e-8 relative bias per K=8 step, 3.8e-5 at K=4096 on all-positive data), so
+    // TMEM only ever accumulates KB_PER_CHUNK k-blocks; the epilogue warps promote
+    // each chunk into round-to-nearest FP32 registers while the next chunk runs in
+    // the other accumulator stage.
     if (lane == 0) {
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; kb++) {
-          mbar_wait(full_bar(stage), phase);
+        for (int kb0 = 0; kb0 < num_kb; kb0 += KB_PER_CHUNK) {
+          mbar_wait(tempty_bar(acc), acc_phase ^ 1);
           tc_fence_after();
-          const uint32_t sa_hi = base + stage * STAGE_BYTES;
-          const uint32_t sa_lo = sa_hi + A_TILE;
-          const uint32_t sb_hi = sa_lo + A_TILE;
-          const uint32_t sb_lo = sb_hi + B_TILE;
+          const uint32_t d_tmem = tmem_base + acc * BN;
+          const int kb1 = min(num_kb, kb0 + KB_PER_CHUNK);
+          for (int kb = kb0; kb < kb1; kb++) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t sa_hi = base + stage * STAGE_BYTES;
+            const uint32_t sa_lo = sa_hi + A_TILE;
+            const uint32_t sb_hi = sa_lo + A_TILE;
+            const uint32_t sb_lo = sb_hi + B_TILE;
 #pragma unroll
-          for (int ks = 0; ks < BK / UMMA_K; ks++) {
-            const uint64_t a_hi = umma_desc(sa_hi + ks * 1024, 4096, 1024);
-            const uint64_t a_lo = umma_desc(sa_lo + ks * 1024, 4096, 1024);
-            const uint64_t b_hi = umma_desc(sb_hi + ks * 32, 16, 1024);
-            const uint64_t b_lo = umma_desc(sb_lo + ks * 32, 16, 1024);
-            umma_tf32(d_tmem, a_lo, b_hi, kIdesc, (kb | ks) != 0);
-            umma_tf32(d_tmem, a_hi, b_lo, kIdesc, 1);
-            umma_tf32(d_tmem, a_hi, b_hi, kIdesc, 1);
+            for (int ks = 0; ks < BK / UMMA_K; ks++) {
+              const uint64_t a_hi = umma_desc(sa_hi + ks * 1024, 4096, 512, kSwizzle128B_Base32B);
+              const uint64_t a_lo = umma_desc(sa_lo + ks * 1024, 4096, 512, kSwizzle128B_Base32B);
+              const uint64_t b_hi = umma_desc(sb_hi + ks * 32, 16, 1024, kSwizzle128B);
+              const uint64_t b_lo = umma_desc(sb_lo + ks * 32, 16, 1024, kSwizzle128B);
+              umma_tf32(d_tmem, a_lo, b_hi, kIdesc, (kb != kb0) || (ks != 0));
+              umma_tf32(d_tmem, a_hi, b_lo, kIdesc, 1);
+              umma_tf32(d_tmem, a_hi, b_hi, kIdesc, 1);
+            }
+            umma_commit(empty_bar(stage));  // frees the smem stage when these MMAs finish
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          umma_commit(empty_bar(stage));  // frees the smem stage when these MMAs finish
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          umma_commit(tfull_bar(acc));  // chunk complete -> epilogue promotes it
+          if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         }
-        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
-        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else if (warp >= 4) {
@@ -282,29 +297,36 @@ sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int m0, n0;
       tile_coords(tile, m0, n0);
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
-      const int row = m0 + q * 32 + lane;
-      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        float v[32];
-        tmem_ld32(taddr + c0, v);
-        if (row < m) {
-          float* cp = C + row + (long long)(n0 + c0) * ldc;
+      float sum[BN];
 #pragma unroll
-          for (int j = 0; j < 32; j++) {
-            if (n0 + c0 + j < n) {
-              const float r = alpha * v[j];
-              cp[j * ldc] = (beta == 0.0f) ? r : r + beta * cp[j * ldc];
-            }
+      for (int j = 0; j < BN; j++) sum[j] = 0.0f;
+      for (int kb0 = 0; kb0 < num_kb; kb0 += KB_PER_CHUNK) {
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          float v[32];
+          tmem_ld32(taddr + c0, v);
+#pragma unroll
+          for (int j = 0; j < 32; j++) sum[c0 + j] += v[j];
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      }
+      const int row = m0 + q * 32 + lane;
+      if (row < m) {
+        float* cp = C + row + (long long)n0 * ldc;
+#pragma unroll
+        for (int j = 0; j < BN; j++) {
+          if (n0 + j < n) {
+            const float r = alpha * sum[j];
+            cp[j * ldc] = (beta == 0.0f) ? r : r + beta * cp[j * ldc];
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
-      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
   }
 
@@ -334,7 +356,7 @@ EncodeTiledFn encode_fn() {
 
 // 2-D fp32 tensor, dim0 contiguous; box {box0, box1}; 128B swizzle; OOB reads give zeros
 int make_map(CUtensorMap* map, const float* ptr, uint64_t dim0, uint64_t dim1, uint64_t ld,
-             uint32_t box0, uint32_t box1) {
+             uint32_t box0, uint32_t box1, CUtensorMapSwizzle swizzle) {
   EncodeTiledFn fn = encode_fn();
   B200_REQUIRE(fn != nullptr, "sgemm_tc: cuTensorMapEncodeTiled is not available from the driver");
   const cuuint64_t dims[2] = {dim0, dim1};
@@ -342,7 +364,7 @@ int make_map(CUtensorMap* map, const float* ptr, uint64_t dim0, uint64_t dim1, u
   const cuuint32_t box[2] = {box0, box1};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   B200_REQUIRE(r == CUDA_SUCCESS, "sgemm_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
   return 0;
@@ -373,10 +395,10 @@ int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const flo
         *b_lo = (float*)(ws + offBlo);
 
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-  if (make_map(&ma_hi, a_hi, m, k, lda, 32, BK)) return 2;
-  if (make_map(&ma_lo, a_lo, m, k, lda, 32, BK)) return 2;
-  if (make_map(&mb_hi, b_hi, k, n, ldb, BK, BN)) return 2;
-  if (make_map(&mb_lo, b_lo, k, n, ldb, BK, BN)) return 2;
+  if (make_map(&ma_hi, a_hi, m, k, lda, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 2;
+  if (make_map(&ma_lo, a_lo, m, k, lda, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 2;
+  if (make_map(&mb_hi, b_hi, k, n, ldb, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B)) return 2;
+  if (make_map(&mb_lo, b_lo, k, n, ldb, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B)) return 2;
 
   const int split_blocks = ctx->sm_count * 8;
   split_tf32_kernel<<<split_blocks, 256, 0, ctx->compute>>>(A, a_hi, a_lo, countA);
