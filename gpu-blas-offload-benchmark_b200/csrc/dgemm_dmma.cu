@@ -10,7 +10,9 @@
 //     tiles -> 64 accumulator doubles per thread, 12 fragment loads per 32 DMMA.
 //   * 3-stage cp.async pipeline (16-byte copies when lda/ldb/pointers allow,
 //     8-byte otherwise), zero-filled at the ragged edges via src-size, so any
-//     m, n, k works without a separate edge kernel.
+//     m, n, k works without a separate edge kernel.  The copies of tile kt+2 are
+//     issued in 8 slices between the DMMA groups of tile kt (never as one burst
+//     after the barrier), and fragments are double-buffered in registers.
 //   * A stage is [k][m] with row stride 132 doubles, B stage is [n][k] with row
 //     stride 36 doubles: both strides are 8 words mod 32 banks, which makes
 //     every fragment LDS.64 of a half-warp (4 k x 4 m|n) conflict-free, and the
@@ -20,6 +22,8 @@
 //     panels in the 126 MB L2.
 //   * split-K with workspace + last-arriving-CTA reduction when the tile count
 //     cannot fill 148 SMs.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -27,7 +31,6 @@ namespace {
 
 constexpr int BM = 128, BN = 128, BK = 32;
 constexpr int STAGES = 3;
-constexpr int NTHREADS = 256;
 constexpr int A_LD = BM + 4;  // doubles; 132*2 words = 8 mod 32
 constexpr int B_LD = BK + 4;  // doubles; 36*2 words  = 8 mod 32
 constexpr int A_STAGE = BK * A_LD;  // doubles
@@ -56,8 +59,13 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
       : "d"(a), "d"(b));
 }
 
-template <bool ALIGNED>
-__global__ void __launch_bounds__(NTHREADS, 1)
+// WARPS_M x WARPS_N warps; each owns a (BM/WARPS_M) x (BN/WARPS_N) warp tile of
+// MI x NI DMMA tiles.  2x4 (64x32 warp tiles) minimises fragment loads; 4x4 (32x32)
+// puts 4 warps on every scheduler, which is what saturates the DMMA pipe: ptxas
+// must separate back-to-back DMMAs of one warp (NOPs in the SASS), so 2 warps per
+// scheduler top out near 79% tensor-pipe utilisation (profiles/r1_dgemm_ncu.md).
+template <bool ALIGNED, int WARPS_M, int WARPS_N>
+__global__ void __launch_bounds__(32 * WARPS_M * WARPS_N, 1)
 dgemm_dmma_kernel(int m, int n, int k, double alpha, const double* __restrict__ A,
                   long long lda, const double* __restrict__ B, long long ldb,
                   double beta, double* __restrict__ C, long long ldc, int tiles_m,
@@ -68,9 +76,12 @@ dgemm_dmma_kernel(int m, int n, int k, double alpha, const double* __restrict__ 
   double* Bs = smem + STAGES * A_STAGE;   // [STAGES][BN][B_LD]
   __shared__ bool is_last;
 
+  constexpr int NTHREADS = 32 * WARPS_M * WARPS_N;
+  constexpr int WTM = BM / WARPS_M, WTN = BN / WARPS_N;  // warp tile
+  constexpr int MI = WTM / 8, NI = WTN / 8;              // DMMA tiles per warp
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
-  const int wm = warp & 1, wn = warp >> 1;  // 2 x 4 warps
+  const int wm = warp % WARPS_M, wn = warp / WARPS_M;
   const int g = lane >> 2, t = lane & 3;
 
   // grouped rasterisation
@@ -93,10 +104,10 @@ dgemm_dmma_kernel(int m, int n, int k, double alpha, const double* __restrict__ 
   // j0, j0+16, ...; per k-tile only the base pointers advance.
   constexpr int A_CHUNKS = (BK * BM / 2) / NTHREADS;  // per thread per tile
   constexpr int B_CHUNKS = (BN * BK / 2) / NTHREADS;
-  const int a_c = tid % (BM / 2), a_p0 = tid / (BM / 2);      // a_p0 in [0,4)
-  const int b_c = tid % (BK / 2), b_j0 = tid / (BK / 2);      // b_j0 in [0,16)
-  constexpr int A_PSTEP = NTHREADS / (BM / 2);                 // 4
-  constexpr int B_JSTEP = NTHREADS / (BK / 2);                 // 16
+  const int a_c = tid % (BM / 2), a_p0 = tid / (BM / 2);
+  const int b_c = tid % (BK / 2), b_j0 = tid / (BK / 2);
+  constexpr int A_PSTEP = NTHREADS / (BM / 2);
+  constexpr int B_JSTEP = NTHREADS / (BK / 2);
   const int a_bytes = max(0, min(2, m - (m0 + 2 * a_c))) * 8;  // m-edge, invariant
   unsigned b_mask = 0;                                         // n-edge, invariant
 #pragma unroll
@@ -107,7 +118,15 @@ dgemm_dmma_kernel(int m, int n, int k, double alpha, const double* __restrict__ 
   const int a_dst = a_p0 * A_LD + 2 * a_c;
   const int b_dst = b_j0 * B_LD + 2 * b_c;
 
-  auto load_tile = [&](int kt, int stage) {
+  // The copies of one k-tile are issued in KSTEPS slices interleaved with the
+  // DMMA groups of the previous tile: issuing all 16 LDGSTS per thread in one burst
+  // right after the barrier occupies the LSU/MIO pipe for ~1000 cycles and starves
+  // the fragment LDS behind it (measured: 29.0 -> 35 TFLOP/s without the burst).
+  constexpr int KSTEPS = BK / 4;
+  auto in_slice = [](int l, int chunks, int part) {
+    return chunks >= KSTEPS ? (l / (chunks / KSTEPS) == part) : (l * (KSTEPS / chunks) == part);
+  };
+  auto load_slice = [&](int kt, int stage, int part) {
     const int kb = kbeg + kt * BK;
     double* as = As + stage * A_STAGE;
     double* bs = Bs + stage * B_STAGE;
@@ -115,30 +134,24 @@ dgemm_dmma_kernel(int m, int n, int k, double alpha, const double* __restrict__ 
       const bool full_k = kb + BK <= kend;
       const double* ap = a_src + (long long)kt * BK * lda;
       const double* bp = b_src + kt * BK;
-      if (full_k) {
 #pragma unroll
-        for (int l = 0; l < A_CHUNKS; l++)
-          cp_async16(as + a_dst + l * A_PSTEP * A_LD, a_bytes ? ap + (long long)l * A_PSTEP * lda : A, a_bytes);
+      for (int l = 0; l < A_CHUNKS; l++) {
+        if (!in_slice(l, A_CHUNKS, part)) continue;
+        const int bytes = (full_k || kb + a_p0 + l * A_PSTEP < kend) ? a_bytes : 0;
+        cp_async16(as + a_dst + l * A_PSTEP * A_LD, bytes ? ap + (long long)l * A_PSTEP * lda : A, bytes);
+      }
 #pragma unroll
-        for (int l = 0; l < B_CHUNKS; l++) {
-          const int bytes = (b_mask >> l) & 1 ? 16 : 0;
-          cp_async16(bs + b_dst + l * B_JSTEP * B_LD, bytes ? bp + (long long)l * B_JSTEP * ldb : B, bytes);
-        }
-      } else {
-#pragma unroll
-        for (int l = 0; l < A_CHUNKS; l++) {
-          const int bytes = (kb + a_p0 + l * A_PSTEP < kend) ? a_bytes : 0;
-          cp_async16(as + a_dst + l * A_PSTEP * A_LD, bytes ? ap + (long long)l * A_PSTEP * lda : A, bytes);
-        }
-#pragma unroll
-        for (int l = 0; l < B_CHUNKS; l++) {
-          int bytes = (b_mask >> l) & 1 ? max(0, min(2, kend - (kb + 2 * b_c))) * 8 : 0;
-          cp_async16(bs + b_dst + l * B_JSTEP * B_LD, bytes ? bp + (long long)l * B_JSTEP * ldb : B, bytes);
-        }
+      for (int l = 0; l < B_CHUNKS; l++) {
+        if (!in_slice(l, B_CHUNKS, part)) continue;
+        int bytes = (b_mask >> l) & 1 ? 16 : 0;
+        if (!full_k && bytes) bytes = max(0, min(2, kend - (kb + 2 * b_c))) * 8;
+        cp_async16(bs + b_dst + l * B_JSTEP * B_LD, bytes ? bp + (long long)l * B_JSTEP * ldb : B, bytes);
       }
     } else {
+      constexpr int A_EL = (BK * BM) / NTHREADS, B_EL = (BN * BK) / NTHREADS;
 #pragma unroll
-      for (int l = 0; l < (BK * BM) / NTHREADS; l++) {
+      for (int l = 0; l < A_EL; l++) {
+        if (!in_slice(l, A_EL, part)) continue;
         const int e = tid + l * NTHREADS;
         const int i = e % BM, p = e / BM;
         const int gi = m0 + i, gp = kb + p;
@@ -146,7 +159,8 @@ dgemm_dmma_kernel(int m, int n, int k, double alpha, const double* __restrict__ 
         cp_async8(as + p * A_LD + i, ok ? A + gi + gp * lda : A, ok ? 8 : 0);
       }
 #pragma unroll
-      for (int l = 0; l < (BN * BK) / NTHREADS; l++) {
+      for (int l = 0; l < B_EL; l++) {
+        if (!in_slice(l, B_EL, part)) continue;
         const int e = tid + l * NTHREADS;
         const int p = e % BK, j = e / BK;
         const int gp = kb + p, gj = n0 + j;
@@ -155,12 +169,16 @@ dgemm_dmma_kernel(int m, int n, int k, double alpha, const double* __restrict__ 
       }
     }
   };
+  auto load_tile = [&](int kt, int stage) {
+#pragma unroll
+    for (int part = 0; part < KSTEPS; part++) load_slice(kt, stage, part);
+  };
 
-  double acc[8][4][2];
+  double acc[MI][NI][2];
 #pragma unroll
-  for (int i = 0; i < 8; i++)
+  for (int i = 0; i < MI; i++)
 #pragma unroll
-    for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < NI; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
 #pragma unroll
   for (int s = 0; s < STAGES - 1; s++) {
@@ -171,25 +189,33 @@ dgemm_dmma_kernel(int m, int n, int k, double alpha, const double* __restrict__ 
   for (int kt = 0; kt < ntiles; kt++) {
     cp_async_wait<STAGES - 2>();
     __syncthreads();
-    {
-      const int nk = kt + STAGES - 1;
-      if (nk < ntiles) load_tile(nk, nk % STAGES);
-      cp_async_commit();
-    }
-    const double* as = As + (kt % STAGES) * A_STAGE + wm * 64 + g;
-    const double* bs = Bs + (kt % STAGES) * B_STAGE + (wn * 32 + g) * B_LD;
+    const int nk = kt + STAGES - 1;
+    const bool do_load = nk < ntiles;
+    const double* as = As + (kt % STAGES) * A_STAGE + wm * WTM + g;
+    const double* bs = Bs + (kt % STAGES) * B_STAGE + (wn * WTN + g) * B_LD;
+    // fragments are double-buffered in registers: the 12 LDS.64 of step k4+1 are
+    // issued before the 32 DMMAs of step k4, so no DMMA ever waits on shared memory
+    double a[2][MI], b[2][NI];
+#pragma unroll
+    for (int mi = 0; mi < MI; mi++) a[0][mi] = as[t * A_LD + mi * 8];
+#pragma unroll
+    for (int ni = 0; ni < NI; ni++) b[0][ni] = bs[ni * 8 * B_LD + t];
 #pragma unroll
     for (int k4 = 0; k4 < BK / 4; k4++) {
-      double a[8], b[4];
+      const int cur = k4 & 1, nxt = cur ^ 1;
+      if (do_load) load_slice(nk, nk % STAGES, k4);
+      if (k4 + 1 < BK / 4) {
 #pragma unroll
-      for (int mi = 0; mi < 8; mi++) a[mi] = as[(k4 * 4 + t) * A_LD + mi * 8];
+        for (int mi = 0; mi < MI; mi++) a[nxt][mi] = as[((k4 + 1) * 4 + t) * A_LD + mi * 8];
 #pragma unroll
-      for (int ni = 0; ni < 4; ni++) b[ni] = bs[ni * 8 * B_LD + k4 * 4 + t];
+        for (int ni = 0; ni < NI; ni++) b[nxt][ni] = bs[ni * 8 * B_LD + (k4 + 1) * 4 + t];
+      }
 #pragma unroll
-      for (int mi = 0; mi < 8; mi++)
+      for (int mi = 0; mi < MI; mi++)
 #pragma unroll
-        for (int ni = 0; ni < 4; ni++) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+        for (int ni = 0; ni < NI; ni++) dmma(acc[mi][ni][0], acc[mi][ni][1], a[cur][mi], b[cur][ni]);
     }
+    cp_async_commit();
   }
   cp_async_wait<0>();
 
@@ -199,12 +225,12 @@ dgemm_dmma_kernel(int m, int n, int k, double alpha, const double* __restrict__ 
     const long long zstride = (long long)gridDim.x * tile_elems;
     double* mine = partial + (long long)blockIdx.y * zstride + (long long)bid * tile_elems;
 #pragma unroll
-    for (int mi = 0; mi < 8; mi++)
+    for (int mi = 0; mi < MI; mi++)
 #pragma unroll
-      for (int ni = 0; ni < 4; ni++)
+      for (int ni = 0; ni < NI; ni++)
 #pragma unroll
         for (int r = 0; r < 2; r++)
-          mine[((mi * 4 + ni) * 2 + r) * NTHREADS + tid] = acc[mi][ni][r];
+          mine[((mi * NI + ni) * 2 + r) * NTHREADS + tid] = acc[mi][ni][r];
     __threadfence();
     __syncthreads();
     if (tid == 0) {
@@ -217,28 +243,28 @@ dgemm_dmma_kernel(int m, int n, int k, double alpha, const double* __restrict__ 
     __threadfence();
     const double* base = partial + (long long)bid * tile_elems;
 #pragma unroll
-    for (int mi = 0; mi < 8; mi++)
+    for (int mi = 0; mi < MI; mi++)
 #pragma unroll
-      for (int ni = 0; ni < 4; ni++)
+      for (int ni = 0; ni < NI; ni++)
 #pragma unroll
         for (int r = 0; r < 2; r++) {
           double s = 0.0;
           for (int z = 0; z < (int)gridDim.y; z++)
-            s += __ldcg(base + z * zstride + ((mi * 4 + ni) * 2 + r) * NTHREADS + tid);
+            s += __ldcg(base + z * zstride + ((mi * NI + ni) * 2 + r) * NTHREADS + tid);
           acc[mi][ni][r] = s;
         }
   }
 
   // epilogue: each accumulator register covers 8 consecutive rows x 4 columns
 #pragma unroll
-  for (int ni = 0; ni < 4; ni++) {
+  for (int ni = 0; ni < NI; ni++) {
 #pragma unroll
     for (int r = 0; r < 2; r++) {
-      const int gj = n0 + wn * 32 + ni * 8 + t * 2 + r;
+      const int gj = n0 + wn * WTN + ni * 8 + t * 2 + r;
       if (gj >= n) continue;
 #pragma unroll
-      for (int mi = 0; mi < 8; mi++) {
-        const int gi = m0 + wm * 64 + mi * 8 + g;
+      for (int mi = 0; mi < MI; mi++) {
+        const int gi = m0 + wm * WTM + mi * 8 + g;
         if (gi >= m) continue;
         double* cp = C + gi + gj * ldc;
         const double v = alpha * acc[mi][ni][r];
@@ -248,7 +274,23 @@ dgemm_dmma_kernel(int m, int n, int k, double alpha, const double* __restrict__ 
   }
 }
 
-bool g_attr_set[2] = {false, false};
+template <bool ALIGNED, int WM, int WN>
+int launch_dmma(b200_ctx* ctx, int m, int n, int k, double alpha, const double* A, int lda,
+                const double* B, int ldb, double beta, double* C, int ldc, int tiles_m, int tiles_n,
+                int splits, int k_per_split, double* partial) {
+  auto kern = dgemm_dmma_kernel<ALIGNED, WM, WN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)(tiles_m * tiles_n), splits);
+  kern<<<grid, 32 * WM * WN, SMEM_BYTES, ctx->compute>>>(
+      m, n, k, alpha, A, (long long)lda, B, (long long)ldb, beta, C, (long long)ldc, tiles_m, tiles_n,
+      k_per_split, partial, ctx->counters);
+  B200_CUDA(cudaGetLastError());
+  return 0;
+}
 
 }  // namespace
 
@@ -264,7 +306,7 @@ int dgemm_dmma_dispatch(b200_ctx* ctx, int m, int n, int k, double alpha,
   int splits = 1;
   if (tiles < ctx->sm_count && tiles <= ctx->num_counters) {
     splits = (int)((ctx->sm_count + tiles - 1) / tiles);
-    const int max_splits = k / (BK * 8);
+    const int max_splits = k / (BK * 4);
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
   }
@@ -276,21 +318,18 @@ int dgemm_dmma_dispatch(b200_ctx* ctx, int m, int n, int k, double alpha,
     partial = (double*)ctx->workspace;
   }
   if (splits > 65535) return -1;
-  auto kern = aligned ? dgemm_dmma_kernel<true> : dgemm_dmma_kernel<false>;
-  if (!g_attr_set[aligned]) {
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)SMEM_BYTES));
-    g_attr_set[aligned] = true;
-  }
-  dim3 grid((unsigned)tiles, splits);
-  kern<<<grid, NTHREADS, SMEM_BYTES, ctx->compute>>>(
-      m, n, k, alpha, A, (long long)lda, B, (long long)ldb, beta, C, (long long)ldc,
-      tiles_m, tiles_n, k_per_split, partial, ctx->counters);
-  B200_CUDA(cudaGetLastError());
-  note_launch(ctx, aligned ? (splits > 1 ? "dgemm_dmma_128x128x32_cp16_splitk"
-                                         : "dgemm_dmma_128x128x32_cp16")
-                           : (splits > 1 ? "dgemm_dmma_128x128x32_cp8_splitk"
-                                         : "dgemm_dmma_128x128x32_cp8"));
+  static const char* env = getenv("B200_DGEMM_WARPS");
+  const bool w8 = !(env && atoi(env) == 16);  // 2x4 warps by default (fewest fragment loads)
+  int rc;
+  if (aligned)
+    rc = w8 ? launch_dmma<true, 2, 4>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tiles_m, tiles_n, splits, k_per_split, partial)
+            : launch_dmma<true, 4, 4>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tiles_m, tiles_n, splits, k_per_split, partial);
+  else
+    rc = w8 ? launch_dmma<false, 2, 4>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tiles_m, tiles_n, splits, k_per_split, partial)
+            : launch_dmma<false, 4, 4>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tiles_m, tiles_n, splits, k_per_split, partial);
+  if (rc) return rc;
+  note_launch(ctx, aligned ? (splits > 1 ? "dgemm_dmma_128x128x32_cp16_splitk" : "dgemm_dmma_128x128x32_cp16")
+                           : (splits > 1 ? "dgemm_dmma_128x128x32_cp8_splitk" : "dgemm_dmma_128x128x32_cp8"));
   return 0;
 }
 
