@@ -306,6 +306,63 @@ def bench_e2e(blob, ctx, kind, dtype, dim, steps, warmup, barrier=lambda: None):
             "launches": launches, "checksum": checksum}
 
 
+def bench_e2e_multi(blob, ctx, torch, dist, kind, dtype, dim, steps, warmup, barrier, rank, world):
+    """N > 1 end to end: every step the replicated operand (A for GEMM, x for GEMV) goes
+    host -> GPU 0 over PCIe and then to every GPU with an NCCL broadcast over NVLink; each
+    rank uploads its own slab (B columns / A rows), runs the kernel and downloads its slab
+    of the result (C columns / y rows) to its own pinned host buffer."""
+    import numpy as np
+    s = ELEM[dtype]
+    tdt = torch.float64 if dtype == "f64" else torch.float32
+    md = blob.OFFLOAD_ONCE
+    rep_count = dim * dim if kind == "gemm" else dim          # A / x
+    slab_count = dim * dim                                    # B slab / A row block
+    out_count = dim * dim if kind == "gemm" else dim          # C slab / y block
+    h_rep, _d = ctx.alloc(md, rep_count * s) if rank == 0 else (None, None)
+    h_slab, d_slab = ctx.alloc(md, slab_count * s)
+    h_out, d_out = ctx.alloc(md, out_count * s)
+    rep_t = torch.zeros(rep_count, dtype=tdt, device="cuda")  # NCCL needs a torch tensor
+    rng = np.random.default_rng(7 + rank)
+    v = blob.host_view(h_slab, slab_count, dtype)
+    for o in range(0, v.size, 1 << 24):
+        v[o:o + (1 << 24)] = rng.integers(0, 100, min(1 << 24, v.size - o)) / (3.0 if kind == "gemm" else 7.0)
+    if rank == 0:
+        vr = blob.host_view(h_rep, rep_count, dtype)
+        for o in range(0, vr.size, 1 << 24):
+            vr[o:o + (1 << 24)] = rng.integers(0, 100, min(1 << 24, vr.size - o)) / (7.0 if kind == "gemm" else 3.0)
+
+    def step():
+        if rank == 0:
+            ctx.h2d(rep_t, h_rep, rep_count * s, 0)
+        ctx.h2d(d_slab, h_slab, slab_count * s, 1)
+        ctx.sync()
+        dist.broadcast(rep_t, src=0)
+        torch.cuda.synchronize()
+        if kind == "gemm":
+            ctx.gemm(dtype, dim, dim, dim, 1.0, rep_t, dim, d_slab, dim, 0.0, d_out, dim)
+        else:
+            ctx.gemv(dtype, dim, dim, 1.0, d_slab, dim, rep_t, 1, 0.0, d_out, 1)
+        ctx.d2h(h_out, d_out, out_count * s, 2)
+        ctx.sync()
+
+    for _ in range(warmup):
+        step()
+    barrier()
+    l0 = ctx.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    barrier()
+    dt = time.perf_counter() - t0
+    launches = ctx.launch_count() - l0
+    if rank == 0:
+        ctx.free(md, h_rep, _d)
+    ctx.free(md, h_slab, d_slab)
+    ctx.free(md, h_out, d_out)
+    h2d = (rep_count + slab_count * world) * s   # whole job: one replicated operand + every slab
+    return {"seconds": dt, "h2d": h2d, "d2h": out_count * s * world, "launches": launches}
+
+
 def run_own_arm(args, kind, dtype, dim):
     import torch
     import torch.distributed as dist
@@ -366,7 +423,10 @@ def run_own_arm(args, kind, dtype, dim):
 
     # --- e2e through the plugin path with host buffers ---------------------
     e2e_steps = max(1, min(args.steps, 5))
-    e = bench_e2e(blob, ctx, kind, dtype, dim, e2e_steps, 1, barrier)
+    if world == 1:
+        e = bench_e2e(blob, ctx, kind, dtype, dim, e2e_steps, 1, barrier)
+    else:
+        e = bench_e2e_multi(blob, ctx, torch, dist, kind, dtype, dim, e2e_steps, 1, barrier, rank, world)
     e_sec = max_over_ranks(e["seconds"])
     e2e_value = (gemm_flops(dim, dim, dim) if kind == "gemm" else gemv_flops(dim, dim)) * world * e2e_steps / e_sec * 1e-9
 
