@@ -39,6 +39,7 @@ SIGNATURES = {
     "b200_ctx_destroy": (_c_int, [_c_void_p]),
     "b200_ctx_set_stream": (_c_int, [_c_void_p, _c_void_p]),
     "b200_ctx_device": (_c_int, [_c_void_p, ctypes.POINTER(_c_int), ctypes.POINTER(_c_int)]),
+    "b200_ctx_set_option": (_c_int, [_c_void_p, ctypes.c_char_p, ctypes.c_char_p]),
     "b200_alloc": (_c_int, [_c_void_p, _c_int, _c_size_t, _pp, _pp]),
     "b200_free": (_c_int, [_c_void_p, _c_int, _c_void_p, _c_void_p]),
     "b200_h2d_async": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_size_t, _c_int]),
@@ -137,6 +138,9 @@ class Context:
     # -- plumbing
     def set_stream(self, cuda_stream):
         _check(self._lib.b200_ctx_set_stream(self._h, cuda_stream))
+
+    def set_option(self, key, value):
+        _check(self._lib.b200_ctx_set_option(self._h, key.encode(), str(value).encode()))
 
     def device(self):
         d, s = ctypes.c_int(), ctypes.c_int()

@@ -54,6 +54,10 @@ struct b200_ctx {
   bool compute_dirty = false;      // kernels issued since the last b200_sync
   bool compute_unordered = false;  // kernels issued since compute_done was recorded
   cudaEvent_t t0 = nullptr, t1 = nullptr;
+  // event ring for the transfer engine (slab / chunk dependencies)
+  static constexpr int kEvPool = 64;
+  cudaEvent_t ev_pool[kEvPool] = {};
+  int ev_pool_size = 0, ev_next = 0;
 
   // scratch: split-K / split-N partials, 3xTF32 operand splits
   void* workspace = nullptr;
@@ -62,8 +66,12 @@ struct b200_ctx {
   unsigned int* counters = nullptr;
   int num_counters = 0;
 
-  std::vector<b200::CachedBlock> pinned_cache, device_cache;  // freed, reusable
-  std::vector<b200::CachedBlock> live_host, live_dev;         // handed out
+  std::vector<b200::CachedBlock> pinned_cache, device_cache, managed_cache;  // freed, reusable
+  std::vector<b200::CachedBlock> live_host, live_dev, live_managed;          // handed out
+
+  // kernel-selection knobs (b200_ctx_set_option)
+  int opt_sgemm = 0;       // 0 auto, 1 tc, 2 ffma
+  int opt_dgemm_tile = 0;  // 0 auto, 64, 128
 
   const char* last_kernel = "none";
   unsigned long long launches = 0;

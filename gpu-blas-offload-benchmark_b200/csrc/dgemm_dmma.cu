@@ -7,7 +7,8 @@
 // FP64 has no tcgen05/TMEM path on Blackwell; the FP64 tensor instruction is
 // warp-level mma.sync m8n8k4 (SASS DMMA.8x8x4).  Structure:
 //   * CTA tile 128x128x32, 8 warps as 2(M) x 4(N), warp tile 64x32 = 8x4 DMMA
-//     tiles -> 64 accumulator doubles per thread, 12 fragment loads per 32 DMMA.
+//     tiles -> 64 accumulator doubles per thread, 12 fragment loads per 32 DMMA
+//     (plus a 64x64x32 / 4-warp config, 2 CTAs per SM, for mid-size problems).
 //   * 3-stage cp.async pipeline (16-byte copies when lda/ldb/pointers allow,
 //     8-byte otherwise), zero-filled at the ragged edges via src-size, so any
 //     m, n, k works without a separate edge kernel.  The copies of tile kt+2 are
@@ -22,6 +23,7 @@
 //     panels in the 126 MB L2.
 //   * split-K with workspace + last-arriving-CTA reduction when the tile count
 //     cannot fill 148 SMs.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -29,14 +31,15 @@
 namespace b200 {
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 32;
+constexpr int BK = 32;
 constexpr int STAGES = 3;
-constexpr int A_LD = BM + 4;  // doubles; 132*2 words = 8 mod 32
-constexpr int B_LD = BK + 4;  // doubles; 36*2 words  = 8 mod 32
-constexpr int A_STAGE = BK * A_LD;  // doubles
-constexpr int B_STAGE = BN * B_LD;
-constexpr size_t SMEM_BYTES = (size_t)STAGES * (A_STAGE + B_STAGE) * sizeof(double);
-static_assert(SMEM_BYTES <= 227 * 1024, "smem budget");
+constexpr int B_LD = BK + 4;  // doubles; 36*2 words = 8 mod 32 banks
+// A rows are BM + 4 doubles: (BM+4)*2 words = 8 mod 32 for BM = 64 and 128
+template <int BM, int BN>
+constexpr size_t smem_bytes() {
+  return (size_t)STAGES * (BK * (BM + 4) + BN * B_LD) * sizeof(double);
+}
+static_assert(smem_bytes<128, 128>() <= 227 * 1024, "smem budget");
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* g, int src_bytes) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -64,13 +67,18 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 // puts 4 warps on every scheduler, which is what saturates the DMMA pipe: ptxas
 // must separate back-to-back DMMAs of one warp (NOPs in the SASS), so 2 warps per
 // scheduler top out near 79% tensor-pipe utilisation (profiles/r1_dgemm_ncu.md).
-template <bool ALIGNED, int WARPS_M, int WARPS_N>
-__global__ void __launch_bounds__(32 * WARPS_M * WARPS_N, 1)
+// Tile configs: 128x128 (1 CTA/SM) for problems with >= one wave of such tiles;
+// 64x64 (4 warps, 2 CTAs/SM) for the mid sizes where the offload threshold lives --
+// 4x the CTAs, so a 256^3 problem spreads over the chip instead of 4 SMs.
+template <bool ALIGNED, int BM, int BN, int WARPS_M, int WARPS_N>
+__global__ void __launch_bounds__(32 * WARPS_M * WARPS_N, (BM * BN <= 64 * 64) ? 2 : 1)
 dgemm_dmma_kernel(int m, int n, int k, double alpha, const double* __restrict__ A,
                   long long lda, const double* __restrict__ B, long long ldb,
                   double beta, double* __restrict__ C, long long ldc, int tiles_m,
                   int tiles_n, int k_per_split, double* __restrict__ partial,
                   unsigned int* __restrict__ counters) {
+  constexpr int A_LD = BM + 4;
+  constexpr int A_STAGE = BK * A_LD, B_STAGE = BN * B_LD;  // doubles
   extern __shared__ __align__(16) double smem[];
   double* As = smem;                      // [STAGES][BK][A_LD]
   double* Bs = smem + STAGES * A_STAGE;   // [STAGES][BN][B_LD]
@@ -242,17 +250,21 @@ dgemm_dmma_kernel(int m, int n, int k, double alpha, const double* __restrict__ 
     if (!is_last) return;
     __threadfence();
     const double* base = partial + (long long)bid * tile_elems;
+    // z outermost: the MI*NI*2 loads of one split are independent and all in flight
+    // together (an inner z loop serialises ~64 dependent L2 round trips: +30 us)
 #pragma unroll
     for (int mi = 0; mi < MI; mi++)
 #pragma unroll
-      for (int ni = 0; ni < NI; ni++)
+      for (int ni = 0; ni < NI; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    for (int z = 0; z < (int)gridDim.y; z++) {
+      const double* src = base + z * zstride + tid;
 #pragma unroll
-        for (int r = 0; r < 2; r++) {
-          double s = 0.0;
-          for (int z = 0; z < (int)gridDim.y; z++)
-            s += __ldcg(base + z * zstride + ((mi * NI + ni) * 2 + r) * NTHREADS + tid);
-          acc[mi][ni][r] = s;
-        }
+      for (int mi = 0; mi < MI; mi++)
+#pragma unroll
+        for (int ni = 0; ni < NI; ni++)
+#pragma unroll
+          for (int r = 0; r < 2; r++) acc[mi][ni][r] += __ldcg(src + ((mi * NI + ni) * 2 + r) * NTHREADS);
+    }
   }
 
   // epilogue: each accumulator register covers 8 consecutive rows x 4 columns
@@ -274,21 +286,44 @@ dgemm_dmma_kernel(int m, int n, int k, double alpha, const double* __restrict__ 
   }
 }
 
-template <bool ALIGNED, int WM, int WN>
+template <bool ALIGNED, int BM, int BN, int WM, int WN>
 int launch_dmma(b200_ctx* ctx, int m, int n, int k, double alpha, const double* A, int lda,
-                const double* B, int ldb, double beta, double* C, int ldc, int tiles_m, int tiles_n,
-                int splits, int k_per_split, double* partial) {
-  auto kern = dgemm_dmma_kernel<ALIGNED, WM, WN>;
+                const double* B, int ldb, double beta, double* C, int ldc, int min_ctas) {
+  const int tiles_m = (m + BM - 1) / BM, tiles_n = (n + BN - 1) / BN;
+  const long long tiles = (long long)tiles_m * tiles_n;
+  if (tiles > 0x7fffffffLL) return -1;
+  int splits = 1;
+  if (tiles < min_ctas && tiles <= ctx->num_counters) {
+    splits = (int)((min_ctas + tiles - 1) / tiles);
+    const int max_splits = k / (BK * 2);  // >= 2 k-tiles per split
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+  }
+  int k_per_split = ((k + splits - 1) / splits + BK - 1) / BK * BK;
+  splits = (k + k_per_split - 1) / k_per_split;
+  if (splits > 65535) return -1;
+  double* partial = nullptr;
+  if (splits > 1) {
+    if (ensure_workspace(ctx, (size_t)splits * tiles * BM * BN * sizeof(double))) return 1;
+    partial = (double*)ctx->workspace;
+  }
+  constexpr size_t SMEM = smem_bytes<BM, BN>();
+  auto kern = dgemm_dmma_kernel<ALIGNED, BM, BN, WM, WN>;
   static bool attr_set = false;
   if (!attr_set) {
-    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     attr_set = true;
   }
-  dim3 grid((unsigned)(tiles_m * tiles_n), splits);
-  kern<<<grid, 32 * WM * WN, SMEM_BYTES, ctx->compute>>>(
+  dim3 grid((unsigned)tiles, splits);
+  kern<<<grid, 32 * WM * WN, SMEM, ctx->compute>>>(
       m, n, k, alpha, A, (long long)lda, B, (long long)ldb, beta, C, (long long)ldc, tiles_m, tiles_n,
       k_per_split, partial, ctx->counters);
   B200_CUDA(cudaGetLastError());
+  static const char* names[2][2] = {{"dgemm_dmma_%dx%dx32_cp8", "dgemm_dmma_%dx%dx32_cp8_splitk"},
+                                    {"dgemm_dmma_%dx%dx32_cp16", "dgemm_dmma_%dx%dx32_cp16_splitk"}};
+  static char name[2][64];
+  snprintf(name[splits > 1], sizeof(name[0]), names[ALIGNED][splits > 1], BM, BN);
+  note_launch(ctx, name[splits > 1]);
   return 0;
 }
 
@@ -297,40 +332,20 @@ int launch_dmma(b200_ctx* ctx, int m, int n, int k, double alpha, const double* 
 int dgemm_dmma_dispatch(b200_ctx* ctx, int m, int n, int k, double alpha,
                         const double* A, int lda, const double* B, int ldb,
                         double beta, double* C, int ldc) {
-  if (m < 64 || n < 64 || k < 16) return -1;  // sub-tile problems: SIMT path
-  const int tiles_m = (m + BM - 1) / BM, tiles_n = (n + BN - 1) / BN;
-  const long long tiles = (long long)tiles_m * tiles_n;
-  if (tiles > 0x7fffffffLL) return -1;
+  if (m < 48 || n < 48 || k < 16) return -1;  // sub-tile problems: SIMT path
   const bool aligned = (lda % 2 == 0) && (ldb % 2 == 0) &&
                        ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0);
-  int splits = 1;
-  if (tiles < ctx->sm_count && tiles <= ctx->num_counters) {
-    splits = (int)((ctx->sm_count + tiles - 1) / tiles);
-    const int max_splits = k / (BK * 4);
-    if (splits > max_splits) splits = max_splits;
-    if (splits < 1) splits = 1;
-  }
-  int k_per_split = ((k + splits - 1) / splits + BK - 1) / BK * BK;
-  splits = (k + k_per_split - 1) / k_per_split;
-  double* partial = nullptr;
-  if (splits > 1) {
-    if (ensure_workspace(ctx, (size_t)splits * tiles * BM * BN * sizeof(double))) return 1;
-    partial = (double*)ctx->workspace;
-  }
-  if (splits > 65535) return -1;
-  static const char* env = getenv("B200_DGEMM_WARPS");
-  const bool w8 = !(env && atoi(env) == 16);  // 2x4 warps by default (fewest fragment loads)
-  int rc;
-  if (aligned)
-    rc = w8 ? launch_dmma<true, 2, 4>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tiles_m, tiles_n, splits, k_per_split, partial)
-            : launch_dmma<true, 4, 4>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tiles_m, tiles_n, splits, k_per_split, partial);
-  else
-    rc = w8 ? launch_dmma<false, 2, 4>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tiles_m, tiles_n, splits, k_per_split, partial)
-            : launch_dmma<false, 4, 4>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tiles_m, tiles_n, splits, k_per_split, partial);
-  if (rc) return rc;
-  note_launch(ctx, aligned ? (splits > 1 ? "dgemm_dmma_128x128x32_cp16_splitk" : "dgemm_dmma_128x128x32_cp16")
-                           : (splits > 1 ? "dgemm_dmma_128x128x32_cp8_splitk" : "dgemm_dmma_128x128x32_cp8"));
-  return 0;
+  const int sms = ctx->sm_count;
+  const long long t128 = (long long)((m + 127) / 128) * ((n + 127) / 128);
+  const int force = ctx->opt_dgemm_tile;  // 64 / 128 force a config (tuning)
+  const bool big = force ? force == 128 : t128 >= sms;
+#define B200_DMMA_ARGS ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc
+  if (big)
+    return aligned ? launch_dmma<true, 128, 128, 2, 4>(B200_DMMA_ARGS, sms)
+                   : launch_dmma<false, 128, 128, 2, 4>(B200_DMMA_ARGS, sms);
+  return aligned ? launch_dmma<true, 64, 64, 2, 2>(B200_DMMA_ARGS, 2 * sms)
+                 : launch_dmma<false, 64, 64, 2, 2>(B200_DMMA_ARGS, 2 * sms);
+#undef B200_DMMA_ARGS
 }
 
 }  // namespace b200

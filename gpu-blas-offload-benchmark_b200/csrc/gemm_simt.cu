@@ -180,14 +180,23 @@ gemm_simt_kernel(int m, int n, int k, T alpha, const T* __restrict__ A,
   __threadfence();
   const long long zstride = (long long)gridDim.x * gridDim.y * tile_elems;
   const T* base = partial + (long long)tile_id * tile_elems;
-  for (int e = tid; e < BM * BN; e += NT) {
-    const int i = e % BM, j = e / BM;
-    const int gi = m0 + i, gj = n0 + j;
+  // z outermost so the EPT loads of one split are independent and in flight together
+  constexpr int EPT = (BM * BN) / NT;
+  T s[EPT];
+#pragma unroll
+  for (int i = 0; i < EPT; i++) s[i] = T(0);
+  for (int z = 0; z < (int)gridDim.z; z++) {
+    const T* src = base + z * zstride + tid;
+#pragma unroll
+    for (int i = 0; i < EPT; i++) s[i] += __ldcg(src + i * NT);
+  }
+#pragma unroll
+  for (int i = 0; i < EPT; i++) {
+    const int e = tid + i * NT;
+    const int gi = m0 + e % BM, gj = n0 + e / BM;
     if (gi >= m || gj >= n) continue;
-    T s = T(0);
-    for (int z = 0; z < (int)gridDim.z; z++) s += __ldcg(base + z * zstride + e);
     T* cp = C + gi + gj * ldc;
-    *cp = (beta == T(0)) ? alpha * s : alpha * s + beta * *cp;
+    *cp = (beta == T(0)) ? alpha * s[i] : alpha * s[i] + beta * *cp;
   }
 }
 

@@ -167,9 +167,19 @@ gemv_n_kernel(int m, int n, T alpha, const T* __restrict__ A, long long lda,
   if (!is_last) return;
   __threadfence();
   if (r < ROWS && grow < m) {
+    // fixed order, but 8 independent loads in flight per step (a plain loop is one
+    // dependent L2 round trip per split)
+    const T* src = partial + blockIdx.x * ROWS + r;
     T total = T(0);
-    for (int s = 0; s < (int)gridDim.y; s++)
-      total += __ldcg(&partial[(long long)s * mpad + blockIdx.x * ROWS + r]);
+    int s = 0;
+    for (; s + 8 <= (int)gridDim.y; s += 8) {
+      T v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) v[u] = __ldcg(src + (long long)(s + u) * mpad);
+#pragma unroll
+      for (int u = 0; u < 8; u++) total += v[u];
+    }
+    for (; s < (int)gridDim.y; s++) total += __ldcg(src + (long long)s * mpad);
     T* yp = y + (long long)grow * incy;
     *yp = (beta == T(0)) ? alpha * total : alpha * total + beta * *yp;
   }

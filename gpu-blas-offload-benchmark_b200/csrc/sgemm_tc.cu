@@ -378,12 +378,12 @@ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const float* A, int lda,
                       const float* B, int ldb, float beta, float* C, int ldc) {
-  static const char* mode = getenv("B200_SGEMM");  // "ffma" forces the SIMT path, "tc" forces this one
-  if (mode && !strcmp(mode, "ffma")) return -1;
-  const bool forced = mode && !strcmp(mode, "tc");
+  if (ctx->opt_sgemm == 2) return -1;  // "ffma" forces the SIMT path, "tc" forces this one
+  const bool forced = ctx->opt_sgemm == 1;
   if ((lda % 4) || (ldb % 4) || ((uintptr_t)A % 16) || ((uintptr_t)B % 16)) return -1;
-  // below ~2 x 128^3 the split pre-pass and descriptor encodes cost more than they save
-  if (!forced && ((double)m * n * k < 4.0e6 || m < 64 || n < 64)) return -1;
+  // below ~512^3 the three launches (two operand splits + GEMM) and four descriptor
+  // encodes cost more than the FFMA path's single launch (measured crossover, size_sweep.py)
+  if (!forced && ((double)m * n * k < 1.0e8 || m < 64 || n < 64)) return -1;
 
   const size_t countA = (size_t)lda * (k - 1) + m, countB = (size_t)ldb * (n - 1) + k;
   const size_t offAlo = align_up(countA * 4, 1024), offBhi = 2 * offAlo;

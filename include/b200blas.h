@@ -58,6 +58,11 @@ int b200_ctx_destroy(b200_ctx* ctx);
  * stream; NULL restores the context's own stream.  Not used by the harness. */
 int b200_ctx_set_stream(b200_ctx* ctx, void* cuda_stream);
 int b200_ctx_device(const b200_ctx* ctx, int* device, int* sm_count);
+/* Kernel-selection knobs (the harness never needs them; tests and tuning do).
+ *   "sgemm"      = "auto" | "tc" (force tcgen05 3xTF32) | "ffma" (force the FP32-pipe path)
+ *   "dgemm_tile" = "auto" | "64" | "128"
+ * Defaults come from the environment at context creation: B200_SGEMM, B200_DGEMM_TILE. */
+int b200_ctx_set_option(b200_ctx* ctx, const char* key, const char* value);
 
 /* ---- memory -------------------------------------------------------------
  * Replaces cudaMallocHost + cudaMalloc (mode once/always, cuBLAS/gemm.hh:76-82)
@@ -111,8 +116,10 @@ int b200_dgemv(b200_ctx* ctx, int trans, int m, int n, double alpha,
  * One whole "always" iteration of the reference (cuBLAS/gemm.hh:124-153,
  * cuBLAS/gemv.hh:120-145): upload A, B/x and C/y from PINNED host memory,
  * compute, download C/y, and return with the result valid on the host.
- * The reference issues these back to back with no overlap; here the operands
- * are cut into column slabs so H2D, compute and D2H overlap on the copy lanes.
+ * The reference issues these back to back with no overlap.  Here large GEMMs
+ * run as a K-chunk pipeline (C = sum_c A(:,Kc) B(Kc,:): chunk c+1 uploads while
+ * chunk c computes; the last chunk is issued per column slab of C so downloads
+ * overlap too), GEMVs stream A in column slabs, small problems go in one shot.
  * h* are host pointers, d* the device buffers from b200_alloc. */
 int b200_sgemm_offload(b200_ctx* ctx, int m, int n, int k, float alpha,
                        const float* hA, float* dA, int lda, const float* hB,

@@ -10,6 +10,15 @@ from test_gpu_parity import run_gemm
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True)
+def force_tensor_core_path(ctx):
+    """Small shapes default to the FFMA path (launch-latency crossover ~512^3);
+    these tests pin the tcgen05 kernel itself."""
+    ctx.set_option("sgemm", "tc")
+    yield
+    ctx.set_option("sgemm", "auto")
+
 SHAPES = [
     (128, 128, 256), (256, 256, 256), (384, 512, 96), (640, 384, 1000), (1024, 1024, 64),
     (260, 132, 200), (1028, 516, 260), (2048, 2048, 32), (512, 64, 4096), (64, 512, 4100),
