@@ -157,6 +157,7 @@ int b200_ctx_create(b200_ctx** out, int device) {
   B200_CUDA(cudaEventCreate(&ctx->t0));
   B200_CUDA(cudaEventCreate(&ctx->t1));
   if (const char* e = getenv("B200_SGEMM")) ctx->opt_sgemm = !strcmp(e, "tc") ? 1 : !strcmp(e, "ffma") ? 2 : 0;
+  if (const char* e = getenv("B200_DGEMM_TMA")) ctx->opt_dgemm_tma = strcmp(e, "off") != 0 && strcmp(e, "0") != 0;
   if (const char* e = getenv("B200_DGEMM_TILE")) ctx->opt_dgemm_tile = atoi(e) == 64 ? 64 : atoi(e) == 128 ? 128 : 0;
   ctx->num_counters = 1 << 16;
   B200_CUDA(cudaMalloc((void**)&ctx->counters, ctx->num_counters * sizeof(unsigned int)));
@@ -207,6 +208,12 @@ int b200_ctx_set_option(b200_ctx* ctx, const char* key, const char* value) {
     else if (!strcmp(value, "64")) ctx->opt_dgemm_tile = 64;
     else if (!strcmp(value, "128")) ctx->opt_dgemm_tile = 128;
     else B200_REQUIRE(false, "b200_ctx_set_option: dgemm_tile must be auto|64|128, got '%s'", value);
+    return 0;
+  }
+  if (!strcmp(key, "dgemm_tma")) {
+    if (!strcmp(value, "on") || !strcmp(value, "auto")) ctx->opt_dgemm_tma = 1;
+    else if (!strcmp(value, "off")) ctx->opt_dgemm_tma = 0;
+    else B200_REQUIRE(false, "b200_ctx_set_option: dgemm_tma must be on|off, got '%s'", value);
     return 0;
   }
   B200_REQUIRE(false, "b200_ctx_set_option: unknown key '%s'", key);

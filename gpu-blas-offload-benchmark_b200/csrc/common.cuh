@@ -72,6 +72,7 @@ struct b200_ctx {
   // kernel-selection knobs (b200_ctx_set_option)
   int opt_sgemm = 0;       // 0 auto, 1 tc, 2 ffma
   int opt_dgemm_tile = 0;  // 0 auto, 64, 128
+  int opt_dgemm_tma = 1;   // 1: large aligned DGEMMs use the TMA-fed kernel, 0: cp.async kernel
 
   const char* last_kernel = "none";
   unsigned long long launches = 0;
@@ -103,6 +104,11 @@ int gemm_simt_dispatch(b200_ctx* ctx, int ta, int tb, int m, int n, int k,
 int dgemm_dmma_dispatch(b200_ctx* ctx, int m, int n, int k, double alpha,
                         const double* A, int lda, const double* B, int ldb,
                         double beta, double* C, int ldc);
+
+// TMA-fed variant of the large-tile DMMA kernel; returns -1 if not eligible.
+int dgemm_tma_dispatch(b200_ctx* ctx, int m, int n, int k, double alpha,
+                       const double* A, int lda, const double* B, int ldb,
+                       double beta, double* C, int ldc);
 
 // 3xTF32 tcgen05/TMEM path; returns -1 if the shape is not eligible.
 int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha,

@@ -340,6 +340,10 @@ int dgemm_dmma_dispatch(b200_ctx* ctx, int m, int n, int k, double alpha,
   const int force = ctx->opt_dgemm_tile;  // 64 / 128 force a config (tuning)
   const bool big = force ? force == 128 : t128 >= sms;
 #define B200_DMMA_ARGS ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc
+  if (big && aligned && ctx->opt_dgemm_tma) {
+    const int rc = dgemm_tma_dispatch(B200_DMMA_ARGS);  // TMA + mbarrier pipeline (dgemm_tma.cu)
+    if (rc >= 0) return rc;
+  }
   if (big)
     return aligned ? launch_dmma<true, 128, 128, 2, 4>(B200_DMMA_ARGS, sms)
                    : launch_dmma<false, 128, 128, 2, 4>(B200_DMMA_ARGS, sms);

@@ -1,0 +1,300 @@
+// dgemm_tma.cu -- large-problem DGEMM: FP64 tensor-core tiles (DMMA.8x8x4) fed by a
+// warp-specialised TMA producer through a 3-stage full/empty mbarrier pipeline into
+// 128-byte-swizzled shared memory.  sm_100a only.
+//
+// Same math and tile shape as dgemm_dmma.cu (128x128x32 CTA tile, 8 consumer warps as
+// 2(M) x 4(N), 64x32 warp tiles); what changes is who moves the data:
+//   * warp 8 is the producer: one lane issues cp.async.bulk.tensor.2d for the whole
+//     stage (8 boxes of A, 2 of B, 64 KB) and arms the stage's `full` mbarrier with the
+//     byte count.  The consumer warps execute no copy instructions at all -- in the
+//     cp.async kernel their LDGSTS bursts competed with the fragment LDS for the LSU
+//     (profiles/r1_ncu_summary.md: 87% DMMA-pipe utilisation).
+//   * there is no __syncthreads in the main loop: a consumer warp waits on full[s],
+//     runs its 256 DMMAs, and one lane arrives on empty[s] (count 8); warps drift
+//     apart freely, so one warp's fragment loads hide behind another's DMMAs.
+//   * TMA writes dense boxes, so padding is impossible; bank conflicts are removed by
+//     the swizzle plus two index permutations that DMMA is indifferent to:
+//       A (M-contiguous): box {16 m, 32 k} -> [k][16 m] rows of 128 B, SWIZZLE_128B
+//         keyed on k mod 8.  The four k of one DMMA are taken as {s, 2+s, 4+s, 6+s}
+//         (s = 0, 1 for the two DMMA steps of an 8-wide k group), which sends the 16
+//         lanes of an LDS.64 half-warp to 16 distinct 8-byte bank pairs.
+//       B (K-contiguous): box {16 k, 128 n} -> [n][16 k] rows of 128 B keyed on n mod 8.
+//         One LDS.128 fetches k = 2j, 2j+1 (both DMMA steps); fragment lane group g
+//         reads column (g&1)*4 + (g>>1) of its 8-column tile so that the 8 lanes of a
+//         quarter-warp cover all 8 16-byte chunks.  The matching column permutation is
+//         applied when C is stored.
+//     (B's k pairing {2j, 2j+1} <-> steps s = 0, 1 is the same k set A uses.)
+//   * out-of-range rows / columns / k are zero-filled by TMA, so ragged edges need no
+//     special code; the only requirement is TMA's: lda, ldb even and 16-byte aligned
+//     bases (otherwise dgemm_dmma.cu's cp.async path runs).
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+#include "tma_host.cuh"
+
+namespace b200 {
+namespace {
+
+using namespace ptx;
+
+constexpr int BM = 128, BN = 128, BK = 32;
+constexpr int STAGES = 3;
+constexpr int CONSUMER_WARPS = 8;
+constexpr int NTHREADS = 32 * (CONSUMER_WARPS + 1);
+constexpr uint32_t A_STAGE_BYTES = (BM / 16) * BK * 128;  // 8 chunks x [32 k][128 B]
+constexpr uint32_t B_STAGE_BYTES = (BK / 16) * BN * 128;  // 2 halves x [128 n][128 B]
+constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 64;
+constexpr int MI = 8, NI = 4;  // DMMA tiles per warp (64 x 32 warp tile)
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile(
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double lds64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ double2 lds128(uint32_t addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+dgemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 int m, int n, int k, double alpha, double beta, double* __restrict__ C, long long ldc,
+                 int tiles_m, int tiles_n, int k_per_split, double* __restrict__ partial,
+                 unsigned int* __restrict__ counters) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + STAGES * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+  __shared__ bool is_last;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+
+  constexpr int GROUP = 8;
+  const int bid = blockIdx.x;
+  const int group_size = GROUP * tiles_n;
+  const int first_m = (bid / group_size) * GROUP;
+  const int gm = min(tiles_m - first_m, GROUP);
+  const int m0 = (first_m + (bid % group_size) % gm) * BM;
+  const int n0 = ((bid % group_size) / gm) * BN;
+  const int kbeg = blockIdx.y * k_per_split;
+  const int kend = min(k, kbeg + k_per_split);
+  const int ntiles = (kend - kbeg + BK - 1) / BK;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), CONSUMER_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == CONSUMER_WARPS) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kt = 0; kt < ntiles; kt++) {
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+        const int kb = kbeg + kt * BK;
+        // A split-K slice must not read past its own k range: the zero fill only covers
+        // k >= K, so the last tile of an inner slice is clipped by the tensor map of the
+        // full matrix -- k_per_split is a multiple of BK, which makes every slice but the
+        // last end on a tile boundary.
+        mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+#pragma unroll
+        for (int c = 0; c < BM / 16; c++) tma_load_2d(sa + c * 4096, &map_a, full_bar(stage), m0 + c * 16, kb);
+#pragma unroll
+        for (int h = 0; h < BK / 16; h++) tma_load_2d(sb + h * 16384, &map_b, full_bar(stage), kb + h * 16, n0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+    // the producer warp takes no part in the epilogue, but must stay for the
+    // block-wide barriers of the split-K reduction below
+  }
+
+  const int wm = warp & 1, wn = (warp >> 1) & 3;
+  const int g = lane >> 2, t = lane & 3;
+  double acc[MI][NI][2];
+#pragma unroll
+  for (int i = 0; i < MI; i++)
+#pragma unroll
+    for (int j = 0; j < NI; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  if (warp < CONSUMER_WARPS) {
+    // ===================== DMMA consumers =====================
+    // A fragment byte offsets inside a stage for (mi parity p, step s); + (mi/2)*4096 + kk*1024
+    uint32_t offA[2][2];
+#pragma unroll
+    for (int p = 0; p < 2; p++)
+#pragma unroll
+      for (int s = 0; s < 2; s++) {
+        const int x = p * 4 + (g >> 1), kq = 2 * t + s;
+        offA[p][s] = (uint32_t)(wm * 4 * 4096 + (g & 1) * 8 + kq * 128 + ((x ^ kq) << 4));
+      }
+    // B fragment byte offsets for even / odd k groups; + ni*1024 + (kk/2)*16384
+    const int rg = (g & 1) * 4 + (g >> 1);  // column of the 8-wide tile this lane group reads
+    const uint32_t offB0 = A_STAGE_BYTES + (uint32_t)((wn * 32 + rg) * 128 + ((t ^ rg) << 4));
+    const uint32_t offB1 = A_STAGE_BYTES + (uint32_t)((wn * 32 + rg) * 128 + (((4 + t) ^ rg) << 4));
+
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kt = 0; kt < ntiles; kt++) {
+      mbar_wait(full_bar(stage), phase);
+      const uint32_t sbase = base + stage * STAGE_BYTES;
+      // register double buffering over the 8 DMMA steps (kk = 0..3, s = 0..1) of the tile
+      double a[2][MI];
+      double2 b2[2][NI];
+#pragma unroll
+      for (int ni = 0; ni < NI; ni++) b2[0][ni] = lds128(sbase + offB0 + ni * 1024);
+#pragma unroll
+      for (int mi = 0; mi < MI; mi++) a[0][mi] = lds64(sbase + offA[mi & 1][0] + (mi >> 1) * 4096);
+#pragma unroll
+      for (int step = 0; step < 8; step++) {
+        const int kk = step >> 1, s = step & 1;
+        const int cur = step & 1, nxt = cur ^ 1;
+        if (step + 1 < 8) {
+          const int kk2 = (step + 1) >> 1, s2 = (step + 1) & 1;
+#pragma unroll
+          for (int mi = 0; mi < MI; mi++)
+            a[nxt][mi] = lds64(sbase + offA[mi & 1][s2] + (mi >> 1) * 4096 + kk2 * 1024);
+          if (s2 == 0) {
+#pragma unroll
+            for (int ni = 0; ni < NI; ni++)
+              b2[kk2 & 1][ni] = lds128(sbase + ((kk2 & 1) ? offB1 : offB0) + ni * 1024 + (kk2 >> 1) * 16384);
+          }
+        }
+#pragma unroll
+        for (int mi = 0; mi < MI; mi++)
+#pragma unroll
+          for (int ni = 0; ni < NI; ni++)
+            dmma(acc[mi][ni][0], acc[mi][ni][1], a[cur][mi], s ? b2[kk & 1][ni].y : b2[kk & 1][ni].x);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_bar(stage));
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+  }
+
+  if (gridDim.y > 1) {
+    // split-K: consumers publish fragment-ordered partials, the last CTA of the tile sums them
+    constexpr int CT = 32 * CONSUMER_WARPS;
+    const long long tile_elems = (long long)BM * BN;
+    const long long zstride = (long long)gridDim.x * tile_elems;
+    if (warp < CONSUMER_WARPS) {
+      double* mine = partial + (long long)blockIdx.y * zstride + (long long)bid * tile_elems;
+#pragma unroll
+      for (int mi = 0; mi < MI; mi++)
+#pragma unroll
+        for (int ni = 0; ni < NI; ni++)
+#pragma unroll
+          for (int r = 0; r < 2; r++) mine[((mi * NI + ni) * 2 + r) * CT + tid] = acc[mi][ni][r];
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned int prev = atomicAdd(&counters[bid], 1u);
+      is_last = (prev == gridDim.y - 1);
+      if (is_last) counters[bid] = 0;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (warp < CONSUMER_WARPS) {
+      const double* src0 = partial + (long long)bid * tile_elems + tid;
+#pragma unroll
+      for (int mi = 0; mi < MI; mi++)
+#pragma unroll
+        for (int ni = 0; ni < NI; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+      for (int z = 0; z < (int)gridDim.y; z++) {
+        const double* src = src0 + z * zstride;
+#pragma unroll
+        for (int mi = 0; mi < MI; mi++)
+#pragma unroll
+          for (int ni = 0; ni < NI; ni++)
+#pragma unroll
+            for (int r = 0; r < 2; r++) acc[mi][ni][r] += __ldcg(src + ((mi * NI + ni) * 2 + r) * CT);
+      }
+    }
+  }
+
+  if (warp >= CONSUMER_WARPS) return;
+  // epilogue: DMMA column (2t + r) of tile ni is matrix column r*4 + t (the B permutation)
+#pragma unroll
+  for (int ni = 0; ni < NI; ni++) {
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      const int gj = n0 + wn * 32 + ni * 8 + r * 4 + t;
+      if (gj >= n) continue;
+#pragma unroll
+      for (int mi = 0; mi < MI; mi++) {
+        const int gi = m0 + wm * 64 + mi * 8 + g;
+        if (gi >= m) continue;
+        double* cp = C + gi + gj * ldc;
+        const double v = alpha * acc[mi][ni][r];
+        *cp = (beta == 0.0) ? v : v + beta * *cp;
+      }
+    }
+  }
+}
+
+bool g_attr_done = false;
+
+}  // namespace
+
+// returns -1 when the shape is not eligible (caller falls back to the cp.async kernel)
+int dgemm_tma_dispatch(b200_ctx* ctx, int m, int n, int k, double alpha, const double* A, int lda,
+                       const double* B, int ldb, double beta, double* C, int ldc) {
+  if ((lda & 1) || (ldb & 1) || ((uintptr_t)A % 16) || ((uintptr_t)B % 16)) return -1;
+  const int tiles_m = (m + BM - 1) / BM, tiles_n = (n + BN - 1) / BN;
+  const long long tiles = (long long)tiles_m * tiles_n;
+  if (tiles > 0x7fffffffLL) return -1;
+  int splits = 1;
+  if (tiles < ctx->sm_count && tiles <= ctx->num_counters) {
+    splits = (int)((ctx->sm_count + tiles - 1) / tiles);
+    const int max_splits = k / (BK * 2);
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+  }
+  int k_per_split = ((k + splits - 1) / splits + BK - 1) / BK * BK;
+  splits = (k + k_per_split - 1) / k_per_split;
+  if (splits > 65535) return -1;
+  double* partial = nullptr;
+  if (splits > 1) {
+    if (ensure_workspace(ctx, (size_t)splits * tiles * BM * BN * sizeof(double))) return 1;
+    partial = (double*)ctx->workspace;
+  }
+  CUtensorMap map_a, map_b;
+  if (make_tensor_map_2d(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, A, m, k, (uint64_t)lda * 8, 16, BK,
+                         CU_TENSOR_MAP_SWIZZLE_128B))
+    return 2;
+  if (make_tensor_map_2d(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, B, k, n, (uint64_t)ldb * 8, 16, BN,
+                         CU_TENSOR_MAP_SWIZZLE_128B))
+    return 2;
+  if (!g_attr_done) {
+    B200_CUDA(cudaFuncSetAttribute(dgemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    g_attr_done = true;
+  }
+  dim3 grid((unsigned)tiles, splits);
+  dgemm_tma_kernel<<<grid, NTHREADS, SMEM_BYTES, ctx->compute>>>(map_a, map_b, m, n, k, alpha, beta, C,
+                                                                 (long long)ldc, tiles_m, tiles_n, k_per_split,
+                                                                 partial, ctx->counters);
+  B200_CUDA(cudaGetLastError());
+  note_launch(ctx, splits > 1 ? "dgemm_dmma_tma_128x128x32_splitk" : "dgemm_dmma_tma_128x128x32");
+  return 0;
+}
+
+}  // namespace b200

@@ -45,6 +45,8 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "ptx.cuh"
+#include "tma_host.cuh"
 
 namespace b200 {
 namespace {
@@ -61,80 +63,7 @@ constexpr uint32_t B_TILE = BN * BK * 4;         // 16 KB: [128 n][128 B]
 constexpr uint32_t STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;
 constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
-// ------------------------------------------------------------ PTX wrappers
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  uint32_t polls = 0;
-  do {
-    asm volatile(
-        "{\n.reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    // a pipeline bug must fault loudly, never hang the GPU
-    if (!done && ++polls > (1u << 28)) __trap();
-  } while (!done);
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
-                                            int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t slot, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(cols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrives on the mbarrier once every previously issued MMA of this thread is done
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
-        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
-        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
-        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
-}
+using namespace ptx;
 
 // UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start>>4  [16,30) LBO>>4  [32,46) SBO>>4  [46,48) version=1  [61,64) layout type
@@ -337,39 +266,6 @@ sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
 
 // ------------------------------------------------------------------- host
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
-                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                  CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)p;
-  }
-  return fn;
-}
-
-// 2-D fp32 tensor, dim0 contiguous; box {box0, box1}; 128B swizzle; OOB reads give zeros
-int make_map(CUtensorMap* map, const float* ptr, uint64_t dim0, uint64_t dim1, uint64_t ld,
-             uint32_t box0, uint32_t box1, CUtensorMapSwizzle swizzle) {
-  EncodeTiledFn fn = encode_fn();
-  B200_REQUIRE(fn != nullptr, "sgemm_tc: cuTensorMapEncodeTiled is not available from the driver");
-  const cuuint64_t dims[2] = {dim0, dim1};
-  const cuuint64_t strides[1] = {ld * sizeof(float)};
-  const cuuint32_t box[2] = {box0, box1};
-  const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  B200_REQUIRE(r == CUDA_SUCCESS, "sgemm_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
-  return 0;
-}
-
 bool g_attr_done = false;
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -395,10 +291,10 @@ int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const flo
         *b_lo = (float*)(ws + offBlo);
 
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-  if (make_map(&ma_hi, a_hi, m, k, lda, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 2;
-  if (make_map(&ma_lo, a_lo, m, k, lda, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 2;
-  if (make_map(&mb_hi, b_hi, k, n, ldb, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B)) return 2;
-  if (make_map(&mb_lo, b_lo, k, n, ldb, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B)) return 2;
+  if (make_tensor_map_2d(&ma_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, a_hi, m, k, (uint64_t)lda * 4, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 2;
+  if (make_tensor_map_2d(&ma_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, a_lo, m, k, (uint64_t)lda * 4, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 2;
+  if (make_tensor_map_2d(&mb_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, b_hi, k, n, (uint64_t)ldb * 4, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B)) return 2;
+  if (make_tensor_map_2d(&mb_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, b_lo, k, n, (uint64_t)ldb * 4, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B)) return 2;
 
   const int split_blocks = ctx->sm_count * 8;
   split_tf32_kernel<<<split_blocks, 256, 0, ctx->compute>>>(A, a_hi, a_lo, countA);

@@ -61,7 +61,9 @@ int b200_ctx_device(const b200_ctx* ctx, int* device, int* sm_count);
 /* Kernel-selection knobs (the harness never needs them; tests and tuning do).
  *   "sgemm"      = "auto" | "tc" (force tcgen05 3xTF32) | "ffma" (force the FP32-pipe path)
  *   "dgemm_tile" = "auto" | "64" | "128"
- * Defaults come from the environment at context creation: B200_SGEMM, B200_DGEMM_TILE. */
+ *   "dgemm_tma"  = "on" | "off"   (large aligned DGEMM: TMA-fed kernel vs cp.async kernel)
+ * Defaults come from the environment at context creation: B200_SGEMM, B200_DGEMM_TILE,
+ * B200_DGEMM_TMA. */
 int b200_ctx_set_option(b200_ctx* ctx, const char* key, const char* value);
 
 /* ---- memory -------------------------------------------------------------
