@@ -157,8 +157,9 @@ int b200_ctx_create(b200_ctx** out, int device) {
   B200_CUDA(cudaEventCreate(&ctx->t0));
   B200_CUDA(cudaEventCreate(&ctx->t1));
   if (const char* e = getenv("B200_SGEMM")) ctx->opt_sgemm = !strcmp(e, "tc") ? 1 : !strcmp(e, "ffma") ? 2 : 0;
+  if (const char* e = getenv("B200_DGEMM_MIN")) ctx->opt_dgemm_min = atoi(e);
   if (const char* e = getenv("B200_DGEMM_TMA")) ctx->opt_dgemm_tma = strcmp(e, "off") != 0 && strcmp(e, "0") != 0;
-  if (const char* e = getenv("B200_DGEMM_TILE")) ctx->opt_dgemm_tile = atoi(e) == 64 ? 64 : atoi(e) == 128 ? 128 : 0;
+  if (const char* e = getenv("B200_DGEMM_TILE")) ctx->opt_dgemm_tile = (atoi(e) == 32 || atoi(e) == 64 || atoi(e) == 128) ? atoi(e) : 0;
   ctx->num_counters = 1 << 16;
   B200_CUDA(cudaMalloc((void**)&ctx->counters, ctx->num_counters * sizeof(unsigned int)));
   B200_CUDA(cudaMemset(ctx->counters, 0, ctx->num_counters * sizeof(unsigned int)));
@@ -205,9 +206,10 @@ int b200_ctx_set_option(b200_ctx* ctx, const char* key, const char* value) {
   }
   if (!strcmp(key, "dgemm_tile")) {
     if (!strcmp(value, "auto")) ctx->opt_dgemm_tile = 0;
+    else if (!strcmp(value, "32")) ctx->opt_dgemm_tile = 32;
     else if (!strcmp(value, "64")) ctx->opt_dgemm_tile = 64;
     else if (!strcmp(value, "128")) ctx->opt_dgemm_tile = 128;
-    else B200_REQUIRE(false, "b200_ctx_set_option: dgemm_tile must be auto|64|128, got '%s'", value);
+    else B200_REQUIRE(false, "b200_ctx_set_option: dgemm_tile must be auto|32|64|128, got '%s'", value);
     return 0;
   }
   if (!strcmp(key, "dgemm_tma")) {
@@ -337,6 +339,14 @@ int b200_prefetch_async(b200_ctx* ctx, const void* managed, size_t bytes, int to
 int b200_advise(b200_ctx* ctx, const void* managed, size_t bytes, int is_input) {
   B200_REQUIRE(ctx && managed, "b200_advise: null argument");
   if (bytes == 0) return 0;
+  // Measured with the unmodified harness (scripts/unified_ab.sh, profiles/r1_unified_ab.txt):
+  // on operands of a few MB the advice costs more than it saves (median 96 vs 63 us per
+  // iteration, worse tails), from ~128 MB it is neutral.  It is therefore applied only to
+  // large operands, where keeping the pages' home on the device protects them from
+  // eviction; B200_ADVISE=all / none overrides.
+  static const char* mode = getenv("B200_ADVISE");
+  if (mode && !strcmp(mode, "none")) return 0;
+  if (!(mode && !strcmp(mode, "all")) && bytes < ((size_t)64 << 20)) return 0;
   B200_CUDA(cudaMemAdvise(managed, bytes, cudaMemAdviseSetPreferredLocation, ctx->device));
   if (is_input) B200_CUDA(cudaMemAdvise(managed, bytes, cudaMemAdviseSetAccessedBy, cudaCpuDeviceId));
   return 0;

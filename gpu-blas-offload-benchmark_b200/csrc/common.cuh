@@ -72,6 +72,7 @@ struct b200_ctx {
   // kernel-selection knobs (b200_ctx_set_option)
   int opt_sgemm = 0;       // 0 auto, 1 tc, 2 ffma
   int opt_dgemm_tile = 0;  // 0 auto, 64, 128
+  int opt_dgemm_min = 48;  // smallest m, n the DMMA kernels take (below: DFMA SIMT path)
   int opt_dgemm_tma = 1;   // 1: large aligned DGEMMs use the TMA-fed kernel, 0: cp.async kernel
 
   const char* last_kernel = "none";

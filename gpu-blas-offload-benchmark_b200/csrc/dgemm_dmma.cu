@@ -34,7 +34,7 @@ namespace {
 constexpr int BK = 32;
 constexpr int STAGES = 3;
 constexpr int B_LD = BK + 4;  // doubles; 36*2 words = 8 mod 32 banks
-// A rows are BM + 4 doubles: (BM+4)*2 words = 8 mod 32 for BM = 64 and 128
+// A rows are BM + 4 doubles: (BM+4)*2 words = 8 mod 32 for BM = 32, 64 and 128
 template <int BM, int BN>
 constexpr size_t smem_bytes() {
   return (size_t)STAGES * (BK * (BM + 4) + BN * B_LD) * sizeof(double);
@@ -67,9 +67,9 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 // puts 4 warps on every scheduler, which is what saturates the DMMA pipe: ptxas
 // must separate back-to-back DMMAs of one warp (NOPs in the SASS), so 2 warps per
 // scheduler top out near 79% tensor-pipe utilisation (profiles/r1_dgemm_ncu.md).
-// Tile configs: 128x128 (1 CTA/SM) for problems with >= one wave of such tiles;
-// 64x64 (4 warps, 2 CTAs/SM) for the mid sizes where the offload threshold lives --
-// 4x the CTAs, so a 256^3 problem spreads over the chip instead of 4 SMs.
+// Tile configs: 128x128 (1 CTA/SM; large unaligned problems -- aligned ones use the
+// TMA-fed twin in dgemm_tma.cu) and 32x32 (4 warps, 4 CTAs/SM) for everything below
+// about one wave of big tiles, where latency and SM coverage matter more than reuse.
 template <bool ALIGNED, int BM, int BN, int WARPS_M, int WARPS_N>
 __global__ void __launch_bounds__(32 * WARPS_M * WARPS_N, (BM * BN <= 64 * 64) ? 2 : 1)
 dgemm_dmma_kernel(int m, int n, int k, double alpha, const double* __restrict__ A,
@@ -288,14 +288,15 @@ dgemm_dmma_kernel(int m, int n, int k, double alpha, const double* __restrict__ 
 
 template <bool ALIGNED, int BM, int BN, int WM, int WN>
 int launch_dmma(b200_ctx* ctx, int m, int n, int k, double alpha, const double* A, int lda,
-                const double* B, int ldb, double beta, double* C, int ldc, int min_ctas) {
+                const double* B, int ldb, double beta, double* C, int ldc, int min_ctas,
+                int min_ktiles_per_split) {
   const int tiles_m = (m + BM - 1) / BM, tiles_n = (n + BN - 1) / BN;
   const long long tiles = (long long)tiles_m * tiles_n;
   if (tiles > 0x7fffffffLL) return -1;
   int splits = 1;
   if (tiles < min_ctas && tiles <= ctx->num_counters) {
     splits = (int)((min_ctas + tiles - 1) / tiles);
-    const int max_splits = k / (BK * 2);  // >= 2 k-tiles per split
+    const int max_splits = k / (BK * min_ktiles_per_split);
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
   }
@@ -332,23 +333,34 @@ int launch_dmma(b200_ctx* ctx, int m, int n, int k, double alpha, const double* 
 int dgemm_dmma_dispatch(b200_ctx* ctx, int m, int n, int k, double alpha,
                         const double* A, int lda, const double* B, int ldb,
                         double beta, double* C, int ldc) {
-  if (m < 48 || n < 48 || k < 16) return -1;  // sub-tile problems: SIMT path
+  if (m < ctx->opt_dgemm_min || n < ctx->opt_dgemm_min || k < 16) return -1;  // sub-tile problems: SIMT path
   const bool aligned = (lda % 2 == 0) && (ldb % 2 == 0) &&
                        ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0);
   const int sms = ctx->sm_count;
   const long long t128 = (long long)((m + 127) / 128) * ((n + 127) / 128);
   const int force = ctx->opt_dgemm_tile;  // 64 / 128 force a config (tuning)
-  const bool big = force ? force == 128 : t128 >= sms;
+  // measured crossover (profiles/r1_size_sweep.txt): from ~100 tiles the 128x128 TMA
+  // kernel (with split-K 2 below one wave) beats the 64x64 config
+  const bool big = force ? force == 128 : t128 * 3 >= sms * 2;
 #define B200_DMMA_ARGS ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc
   if (big && aligned && ctx->opt_dgemm_tma) {
     const int rc = dgemm_tma_dispatch(B200_DMMA_ARGS);  // TMA + mbarrier pipeline (dgemm_tma.cu)
     if (rc >= 0) return rc;
   }
   if (big)
-    return aligned ? launch_dmma<true, 128, 128, 2, 4>(B200_DMMA_ARGS, sms)
-                   : launch_dmma<false, 128, 128, 2, 4>(B200_DMMA_ARGS, sms);
-  return aligned ? launch_dmma<true, 64, 64, 2, 2>(B200_DMMA_ARGS, 2 * sms)
-                 : launch_dmma<false, 64, 64, 2, 2>(B200_DMMA_ARGS, 2 * sms);
+    return aligned ? launch_dmma<true, 128, 128, 2, 4>(B200_DMMA_ARGS, sms, 2)
+                   : launch_dmma<false, 128, 128, 2, 4>(B200_DMMA_ARGS, sms, 2);
+  // Everything below one wave of 128x128 tiles runs on 32x32 tiles (4 warps of 16x16,
+  // up to 4 CTAs/SM, split-K down to one k-tile per CTA): a 64^3 problem spreads over
+  // 8 SMs, a 128^3 one over 64, and the kernel is one load, 32 DMMAs per warp and the
+  // last-CTA reduction.  Measured GPU-side durations (ncu, profiles/r1_size_sweep.txt):
+  // 4.7 us at 48^3, 6.7 us at 128^3, 96 us at 1024^3 -- faster than the 64x64 config
+  // everywhere up to the 128x128 crossover, so 64x64 is kept only as a forced option.
+  if (force == 64)
+    return aligned ? launch_dmma<true, 64, 64, 2, 2>(B200_DMMA_ARGS, 2 * sms, 2)
+                   : launch_dmma<false, 64, 64, 2, 2>(B200_DMMA_ARGS, 2 * sms, 2);
+  return aligned ? launch_dmma<true, 32, 32, 2, 2>(B200_DMMA_ARGS, 2 * sms, 1)
+                 : launch_dmma<false, 32, 32, 2, 2>(B200_DMMA_ARGS, 2 * sms, 1);
 #undef B200_DMMA_ARGS
 }
 

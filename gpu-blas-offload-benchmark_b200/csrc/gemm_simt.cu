@@ -15,6 +15,8 @@
 //     bank groups (no conflicts) and C stores stay coalesced along M.
 //   * split-K over blockIdx.z with a workspace + last-arriving-CTA reduction
 //     in fixed order: deterministic, single launch.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -218,7 +220,7 @@ int launch_simt(b200_ctx* ctx, int m, int n, int k, T alpha, const T* A,
   int splits = 1;
   if (tiles < want_ctas && tiles <= ctx->num_counters) {
     splits = (int)((want_ctas + tiles - 1) / tiles);
-    const int max_splits = k / (Cfg::BK * 8);  // >= 8 k-tiles per split
+    const int max_splits = k / (Cfg::BK * 2);  // >= 2 k-tiles per split (latency regime)
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
   }
@@ -271,6 +273,11 @@ int gemm_simt_dispatch(b200_ctx* ctx, int ta, int tb, int m, int n, int k,
   if (m >= 96 && n >= 96 && t128 >= sms)
     return launch_simt<T, Big>(ctx, m, n, k, alpha, A, sa_i, sa_p, B, sb_p, sb_j,
                                beta, C, ldc, sms, F ? "sgemm_ffma_128x128" : "dgemm_dfma_128x128");
+  static const char* simt_env = getenv("B200_SIMT_SMALL");  // tuning: t64 limit for the 32x32 config
+  const long long small_limit = simt_env ? atoll(simt_env) : 16;  // <= 256^2: measured (ncu durations)
+  if (t64 <= small_limit)
+    return launch_simt<T, Small>(ctx, m, n, k, alpha, A, sa_i, sa_p, B, sb_p, sb_j,
+                                 beta, C, ldc, 4 * sms, F ? "sgemm_ffma_32x32" : "dgemm_dfma_32x32");
   if (m > 32 && n > 32 && t64 * 4 >= sms)
     return launch_simt<T, Mid>(ctx, m, n, k, alpha, A, sa_i, sa_p, B, sb_p, sb_j,
                                beta, C, ldc, 2 * sms, F ? "sgemm_ffma_64x64" : "dgemm_dfma_64x64");

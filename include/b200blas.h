@@ -60,7 +60,7 @@ int b200_ctx_set_stream(b200_ctx* ctx, void* cuda_stream);
 int b200_ctx_device(const b200_ctx* ctx, int* device, int* sm_count);
 /* Kernel-selection knobs (the harness never needs them; tests and tuning do).
  *   "sgemm"      = "auto" | "tc" (force tcgen05 3xTF32) | "ffma" (force the FP32-pipe path)
- *   "dgemm_tile" = "auto" | "64" | "128"
+ *   "dgemm_tile" = "auto" | "32" | "64" | "128"
  *   "dgemm_tma"  = "on" | "off"   (large aligned DGEMM: TMA-fed kernel vs cp.async kernel)
  * Defaults come from the environment at context creation: B200_SGEMM, B200_DGEMM_TILE,
  * B200_DGEMM_TMA. */
@@ -83,10 +83,10 @@ int b200_h2d_async(b200_ctx* ctx, void* dev, const void* host, size_t bytes, int
 int b200_d2h_async(b200_ctx* ctx, void* host, const void* dev, size_t bytes, int lane);
 int b200_prefetch_async(b200_ctx* ctx, const void* managed, size_t bytes,
                         int to_device, int lane);
-/* Unified-mode placement policy the reference lacks:
- * read_mostly != 0 marks an input operand (cudaMemAdviseSetReadMostly is NOT
- * used -- it duplicates pages; we set preferred location = device and
- * accessed-by = CPU); output operands get preferred location = device only. */
+/* Unified-mode placement policy the reference lacks: preferred
+ * location = device (+ accessed-by = CPU for inputs; cudaMemAdviseSetReadMostly is NOT
+ * used -- it duplicates pages).  Applied to operands >= 64 MiB only: on small operands
+ * the advice measurably slows the harness' unified rows (scripts/unified_ab.sh). */
 int b200_advise(b200_ctx* ctx, const void* managed, size_t bytes, int is_input);
 
 /* Replaces cudaDeviceSynchronize (cuBLAS/gemm.hh:152,207,215): returns once

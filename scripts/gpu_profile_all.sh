@@ -3,7 +3,7 @@
 TAG=${1:-prof}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
-for spec in "dgemm:dgemm_dmma" "sgemm:sgemm_3xtf32" "dgemv:gemv_n" "sgemv:gemv_n"; do
+for spec in ${SPECS:-"dgemm:dgemm_tma" "sgemm:sgemm_3xtf32" "dgemv:gemv_n" "sgemv:gemv_n"}; do
   wl=${spec%%:*}; kr=${spec##*:}
   CMD="python bench.py --steps 2 --warmup 3 --no-extras --workload $wl"
   $CMD > $OUT/${wl}_plain.log 2>&1 &&
