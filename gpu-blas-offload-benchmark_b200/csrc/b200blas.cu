@@ -72,10 +72,11 @@ static size_t round_capacity(size_t bytes) {
   return (bytes + gran - 1) / gran * gran;
 }
 
-static void* cache_take(std::vector<CachedBlock>& cache, size_t cap) {
+static void* cache_take(std::vector<CachedBlock>& cache, size_t cap, void** alias = nullptr) {
   for (size_t i = 0; i < cache.size(); i++) {
     if (cache[i].capacity == cap) {
       void* p = cache[i].ptr;
+      if (alias) *alias = cache[i].alias;
       cache.erase(cache.begin() + i);
       return p;
     }
@@ -85,12 +86,12 @@ static void* cache_take(std::vector<CachedBlock>& cache, size_t cap) {
 
 template <typename FreeFn>
 static void cache_put(std::vector<CachedBlock>& cache, void* p, size_t cap,
-                      size_t max_total, FreeFn free_fn) {
+                      size_t max_total, FreeFn free_fn, void* alias = nullptr) {
   if (cap > max_total) {
     free_fn(p);
     return;
   }
-  cache.push_back({p, cap});
+  cache.push_back({p, cap, alias});
   size_t total = 0;
   for (auto& b : cache) total += b.capacity;
   while (cache.size() > 12 || total > max_total) {
@@ -101,14 +102,26 @@ static void cache_put(std::vector<CachedBlock>& cache, void* p, size_t cap,
 }
 
 // capacity bookkeeping for live blocks (ptr -> capacity)
-static size_t live_pop(std::vector<CachedBlock>& v, void* p) {
+static size_t live_pop(std::vector<CachedBlock>& v, void* p, void** alias = nullptr) {
   for (size_t i = 0; i < v.size(); i++)
     if (v[i].ptr == p) {
       const size_t c = v[i].capacity;
+      if (alias) *alias = v[i].alias;
       v.erase(v.begin() + i);
       return c;
     }
   return 0;
+}
+
+// Device-side address of a pinned host pointer handed out by b200_alloc (nullptr if the
+// pointer is not ours -- then the zero-copy path is not taken).
+static void* device_alias(const b200_ctx* ctx, const void* host) {
+  for (const auto& b : ctx->live_host) {
+    const char* base = (const char*)b.ptr;
+    if ((const char*)host >= base && (const char*)host < base + b.capacity && b.alias)
+      return (char*)b.alias + ((const char*)host - base);
+  }
+  return nullptr;
 }
 
 }  // namespace b200
@@ -157,6 +170,8 @@ int b200_ctx_create(b200_ctx** out, int device) {
   B200_CUDA(cudaEventCreate(&ctx->t0));
   B200_CUDA(cudaEventCreate(&ctx->t1));
   if (const char* e = getenv("B200_SGEMM")) ctx->opt_sgemm = !strcmp(e, "tc") ? 1 : !strcmp(e, "ffma") ? 2 : 0;
+  if (const char* e = getenv("B200_ZEROCOPY_GEMM_BYTES")) ctx->opt_zerocopy_gemm_bytes = (size_t)atoll(e);
+  if (const char* e = getenv("B200_ZEROCOPY_GEMV_BYTES")) ctx->opt_zerocopy_gemv_bytes = (size_t)atoll(e);
   if (const char* e = getenv("B200_DGEMM_MIN")) ctx->opt_dgemm_min = atoi(e);
   if (const char* e = getenv("B200_DGEMM_TMA")) ctx->opt_dgemm_tma = strcmp(e, "off") != 0 && strcmp(e, "0") != 0;
   if (const char* e = getenv("B200_DGEMM_TILE")) ctx->opt_dgemm_tile = (atoi(e) == 32 || atoi(e) == 64 || atoi(e) == 128) ? atoi(e) : 0;
@@ -251,8 +266,16 @@ int b200_alloc(b200_ctx* ctx, int mode, size_t bytes, void** host, void** dev) {
   // operand splits need 2 x (|A| + |B|), split-K partials far less.
   if (ensure_workspace(ctx, std::min<size_t>(4 * bytes + ((size_t)32 << 20), (size_t)24 << 30))) return 1;
   const size_t cap = round_capacity(bytes);
-  void* h = cache_take(ctx->pinned_cache, cap);
-  if (!h) B200_CUDA(cudaMallocHost(&h, cap));
+  void* alias = nullptr;
+  void* h = cache_take(ctx->pinned_cache, cap, &alias);
+  if (!h) {
+    B200_CUDA(cudaMallocHost(&h, cap));
+    // under UVA pinned memory is mapped into the device address space (zero-copy path)
+    if (cudaHostGetDevicePointer(&alias, h, 0) != cudaSuccess) {
+      alias = nullptr;
+      cudaGetLastError();
+    }
+  }
   void* d = cache_take(ctx->device_cache, cap);
   if (!d) {
     cudaError_t e = cudaMalloc(&d, cap);
@@ -262,7 +285,7 @@ int b200_alloc(b200_ctx* ctx, int mode, size_t bytes, void** host, void** dev) {
       return 1;
     }
   }
-  ctx->live_host.push_back({h, cap});
+  ctx->live_host.push_back({h, cap, alias});
   ctx->live_dev.push_back({d, cap});
   *host = h;
   *dev = d;
@@ -286,9 +309,10 @@ int b200_free(b200_ctx* ctx, int mode, void* host, void* dev) {
   if (ctx->compute_dirty || ctx->lane_dirty[0] || ctx->lane_dirty[1] || ctx->lane_dirty[2])
     if (b200_sync(ctx)) return 1;
   if (host) {
-    const size_t cap = live_pop(ctx->live_host, host);
+    void* alias = nullptr;
+    const size_t cap = live_pop(ctx->live_host, host, &alias);
     if (cap)
-      cache_put(ctx->pinned_cache, host, cap, (size_t)6 << 30, [](void* p) { cudaFreeHost(p); });
+      cache_put(ctx->pinned_cache, host, cap, (size_t)6 << 30, [](void* p) { cudaFreeHost(p); }, alias);
     else
       B200_CUDA(cudaFreeHost(host));
   }
@@ -478,6 +502,19 @@ int gemm_offload(b200_ctx* ctx, int m, int n, int k, T alpha, const T* hA, T* dA
   // ---- small problems: one shot, fewest API calls (latency matters, not overlap).
   // C is only uploaded when beta != 0 -- with beta == 0 BLAS never reads it, so the
   // reference's third upload (cuBLAS/gemm.hh:130-131) is dead traffic.
+  if (bytesA + bytesB + bytesC <= ctx->opt_zerocopy_gemm_bytes) {
+    // ---- tiny problems: zero copy.  The kernel reads A and B straight from pinned host
+    // memory over PCIe and writes C back the same way: one launch + one stream sync
+    // instead of two uploads, a launch, a download and a sync.
+    const T* zA = (const T*)device_alias(ctx, hA);
+    const T* zB = (const T*)device_alias(ctx, hB);
+    T* zC = (T*)device_alias(ctx, hC);
+    if (zA && zB && zC) {
+      if (engine_begin(ctx)) return 1;
+      if (gemm(ctx, 0, 0, m, n, k, alpha, zA, lda, zB, ldb, beta, zC, ldc)) return 1;
+      return b200_sync(ctx);
+    }
+  }
   if (bytesA + bytesB + bytesC < ((size_t)16 << 20) || k == 0) {
     if (b200_h2d_async(ctx, dA, hA, bytesA, 0)) return 1;
     if (b200_h2d_async(ctx, dB, hB, bytesB, 1)) return 1;
@@ -645,6 +682,16 @@ int gemv_offload(b200_ctx* ctx, int m, int n, T alpha, const T* hA, T* dA, int l
   if (m == 0) return 0;
   const size_t s = sizeof(T);
   const size_t bytesA = s * (size_t)lda * n;
+  if (bytesA <= ctx->opt_zerocopy_gemv_bytes) {  // zero copy, see gemm_offload
+    const T* zA = (const T*)device_alias(ctx, hA);
+    const T* zx = (const T*)device_alias(ctx, hx);
+    T* zy = (T*)device_alias(ctx, hy);
+    if (zA && zx && zy) {
+      if (engine_begin(ctx)) return 1;
+      if (gemv(ctx, 0, m, n, alpha, zA, lda, zx, 1, beta, zy, 1)) return 1;
+      return b200_sync(ctx);
+    }
+  }
   if (bytesA < ((size_t)8 << 20) || n < 2) {  // one shot
     if (b200_h2d_async(ctx, dA, hA, n ? s * ((size_t)lda * (n - 1) + m) : 0, 0)) return 1;
     if (b200_h2d_async(ctx, dx, hx, s * (size_t)n, 1)) return 1;

@@ -35,6 +35,7 @@ void set_error(const char* fmt, ...);
 struct CachedBlock {
   void* ptr;
   size_t capacity;
+  void* alias = nullptr;  // pinned host blocks: the address the DEVICE uses for the same memory
 };
 
 }  // namespace b200
@@ -72,6 +73,11 @@ struct b200_ctx {
   // kernel-selection knobs (b200_ctx_set_option)
   int opt_sgemm = 0;       // 0 auto, 1 tc, 2 ffma
   int opt_dgemm_tile = 0;  // 0 auto, 64, 128
+  // Always mode: operand sets up to these sizes are computed in place from pinned host
+  // memory (measured break-evens, scripts/zerocopy_ab.sh: GEMM re-reads tiles over PCIe,
+  // GEMV touches every element once)
+  size_t opt_zerocopy_gemm_bytes = 200u << 10;
+  size_t opt_zerocopy_gemv_bytes = 16u << 20;
   int opt_dgemm_min = 48;  // smallest m, n the DMMA kernels take (below: DFMA SIMT path)
   int opt_dgemm_tma = 1;   // 1: large aligned DGEMMs use the TMA-fed kernel, 0: cp.async kernel
 
