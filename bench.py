@@ -193,8 +193,9 @@ def run_reference_arm(args, kind, dtype, dim):
         "metric": f"{'D' if dtype == 'f64' else 'S'}{kind.upper()} GFLOP/s (GPU-BLOB formula)",
         "value": r["value"], "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
-        "config": workload_config(kind, dtype, dim, args.gpus),
+        "scaling": "strong" if (args.strong and args.gpus > 1) else "weak", "vs_baseline": None,
+        "dtype": dtype, "data": "synthetic",
+        "config": workload_config(kind, dtype, dim, args.gpus, args.strong),
         "cpu_baseline": {"value": r["value"], "unit": "GFLOP/s", "cores": r["cores"],
                          "kind": r["kind"], "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -205,9 +206,13 @@ def run_reference_arm(args, kind, dtype, dim):
 
 # ------------------------------------------------------------------- own arm
 
-def workload_config(kind, dtype, dim, gpus):
+def workload_config(kind, dtype, dim, gpus, strong=False):
     p = "d" if dtype == "f64" else "s"
-    if kind == "gemm":
+    if gpus > 1 and strong:
+        wl = (f"{p}gemm M=N=K={dim} in {gpus} column slabs ({dim // gpus} columns of B and C per GPU, A replicated)"
+              if kind == "gemm" else
+              f"{p}gemv M=N={dim} in {gpus} row blocks ({dim // gpus} rows of A and y per GPU, x replicated)")
+    elif kind == "gemm":
         wl = f"{p}gemm_square M=N=K={dim}" if gpus == 1 else \
             f"{p}gemm column slabs: M=K={dim}, N={dim}x{gpus} ({dim} columns of B and C per GPU, A replicated)"
     else:
@@ -219,15 +224,18 @@ def workload_config(kind, dtype, dim, gpus):
             "inputs": "rand()%100 / 7.0 and / 3.0 value distribution of the reference generator"}
 
 
-def device_inputs(torch, kind, dtype, dim, seed):
+def device_inputs(torch, kind, dtype, dim, seed, loc=None):
+    """loc = this rank's extent of the partitioned dimension (columns of B/C for GEMM,
+    rows of A/y for GEMV); dim when there is one rank or the scaling is weak."""
+    loc = loc or dim
     tdt = torch.float64 if dtype == "f64" else torch.float32
     g = torch.Generator(device="cuda").manual_seed(seed)
 
     def fill(count, div):
         return torch.randint(0, 100, (count,), generator=g, device="cuda").to(tdt) / div
     if kind == "gemm":
-        return fill(dim * dim, 7.0), fill(dim * dim, 3.0), torch.zeros(dim * dim, dtype=tdt, device="cuda")
-    return fill(dim * dim, 7.0), fill(dim, 3.0), torch.zeros(dim, dtype=tdt, device="cuda")
+        return fill(dim * dim, 7.0), fill(dim * loc, 3.0), torch.zeros(dim * loc, dtype=tdt, device="cuda")
+    return fill(loc * dim, 7.0), fill(dim, 3.0), torch.zeros(loc, dtype=tdt, device="cuda")
 
 
 def time_device(ctx, call, steps, warmup, barrier):
@@ -306,7 +314,7 @@ def bench_e2e(blob, ctx, kind, dtype, dim, steps, warmup, barrier=lambda: None):
             "launches": launches, "checksum": checksum}
 
 
-def bench_e2e_multi(blob, ctx, torch, dist, kind, dtype, dim, steps, warmup, barrier, rank, world):
+def bench_e2e_multi(blob, ctx, torch, dist, kind, dtype, dim, steps, warmup, barrier, rank, world, loc):
     """N > 1 end to end: every step the replicated operand (A for GEMM, x for GEMV) goes
     host -> GPU 0 over PCIe and then to every GPU with an NCCL broadcast over NVLink; each
     rank uploads its own slab (B columns / A rows), runs the kernel and downloads its slab
@@ -316,8 +324,8 @@ def bench_e2e_multi(blob, ctx, torch, dist, kind, dtype, dim, steps, warmup, bar
     tdt = torch.float64 if dtype == "f64" else torch.float32
     md = blob.OFFLOAD_ONCE
     rep_count = dim * dim if kind == "gemm" else dim          # A / x
-    slab_count = dim * dim                                    # B slab / A row block
-    out_count = dim * dim if kind == "gemm" else dim          # C slab / y block
+    slab_count = dim * loc                                    # B slab / A row block
+    out_count = dim * loc if kind == "gemm" else loc          # C slab / y block
     h_rep, _d = ctx.alloc(md, rep_count * s) if rank == 0 else (None, None)
     h_slab, d_slab = ctx.alloc(md, slab_count * s)
     h_out, d_out = ctx.alloc(md, out_count * s)
@@ -339,9 +347,9 @@ def bench_e2e_multi(blob, ctx, torch, dist, kind, dtype, dim, steps, warmup, bar
         dist.broadcast(rep_t, src=0)
         torch.cuda.synchronize()
         if kind == "gemm":
-            ctx.gemm(dtype, dim, dim, dim, 1.0, rep_t, dim, d_slab, dim, 0.0, d_out, dim)
+            ctx.gemm(dtype, dim, loc, dim, 1.0, rep_t, dim, d_slab, dim, 0.0, d_out, dim)
         else:
-            ctx.gemv(dtype, dim, dim, 1.0, d_slab, dim, rep_t, 1, 0.0, d_out, 1)
+            ctx.gemv(dtype, loc, dim, 1.0, d_slab, loc, rep_t, 1, 0.0, d_out, 1)
         ctx.d2h(h_out, d_out, out_count * s, 2)
         ctx.sync()
 
@@ -391,7 +399,8 @@ def run_own_arm(args, kind, dtype, dim):
         return float(t.item())
 
     # --- headline: device resident ---------------------------------------
-    a, b, c = device_inputs(torch, kind, dtype, dim, seed=1 + rank if kind == "gemv" else 1)
+    loc = dim // world if (args.strong and world > 1) else dim
+    a, b, c = device_inputs(torch, kind, dtype, dim, seed=1 + rank if kind == "gemv" else 1, loc=loc)
     if world > 1:
         # the replicated operand travels over NVLink once (A for GEMM, x for GEMV);
         # the slab operands (B, C columns / A, y rows) are generated per rank
@@ -399,14 +408,14 @@ def run_own_arm(args, kind, dtype, dim):
         dist.broadcast(rep, src=0)
         if kind == "gemm":
             g = torch.Generator(device="cuda").manual_seed(100 + rank)
-            b = torch.randint(0, 100, (dim * dim,), generator=g, device="cuda").to(b.dtype) / 3.0
+            b = torch.randint(0, 100, (dim * loc,), generator=g, device="cuda").to(b.dtype) / 3.0
     torch.cuda.synchronize()
     if kind == "gemm":
-        call = lambda: ctx.gemm(dtype, dim, dim, dim, 1.0, a, dim, b, dim, 0.0, c, dim)
-        flops, nbytes = gemm_flops(dim, dim, dim), gemm_bytes(dim, dim, dim, ELEM[dtype])
+        call = lambda: ctx.gemm(dtype, dim, loc, dim, 1.0, a, dim, b, dim, 0.0, c, dim)
+        flops, nbytes = gemm_flops(dim, loc, dim), gemm_bytes(dim, loc, dim, ELEM[dtype])
     else:
-        call = lambda: ctx.gemv(dtype, dim, dim, 1.0, a, dim, b, 1, 0.0, c, 1)
-        flops, nbytes = gemv_flops(dim, dim), gemv_bytes(dim, dim, ELEM[dtype])
+        call = lambda: ctx.gemv(dtype, loc, dim, 1.0, a, loc, b, 1, 0.0, c, 1)
+        flops, nbytes = gemv_flops(loc, dim), gemv_bytes(loc, dim, ELEM[dtype])
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -426,9 +435,9 @@ def run_own_arm(args, kind, dtype, dim):
     if world == 1:
         e = bench_e2e(blob, ctx, kind, dtype, dim, e2e_steps, 1, barrier)
     else:
-        e = bench_e2e_multi(blob, ctx, torch, dist, kind, dtype, dim, e2e_steps, 1, barrier, rank, world)
+        e = bench_e2e_multi(blob, ctx, torch, dist, kind, dtype, dim, e2e_steps, 1, barrier, rank, world, loc)
     e_sec = max_over_ranks(e["seconds"])
-    e2e_value = (gemm_flops(dim, dim, dim) if kind == "gemm" else gemv_flops(dim, dim)) * world * e2e_steps / e_sec * 1e-9
+    e2e_value = flops * world * e2e_steps / e_sec * 1e-9
 
     if rank != 0:
         ctx.close()
@@ -439,19 +448,28 @@ def run_own_arm(args, kind, dtype, dim):
 
     # --- roofline of the dominant kernel -----------------------------------
     peaks, peak_src = measured_peaks()
-    if kind == "gemm":
-        probe = "dmma" if dtype == "f64" else "ffma"
-        pk = ctx.probe_peak(probe)  # GFLOP/s, measured live on this GPU
-        pk2 = ctx.probe_peak("dfma") if dtype == "f64" else None
-        peak = max(pk, pk2 or 0.0)
-        roofline = {"bound": "tensor" if dtype == "f64" else "fp32-pipe", "achieved": per_gpu_gflops / 1e3,
+    if kind == "gemm" and dtype == "f64":
+        pk = ctx.probe_peak("dmma")  # GFLOP/s, measured live on this GPU
+        pk2 = ctx.probe_peak("dfma")
+        peak = max(pk, pk2)
+        roofline = {"bound": "tensor", "achieved": per_gpu_gflops / 1e3, "peak": peak / 1e3, "unit": "TFLOP/s",
+                    "frac": per_gpu_gflops / peak, "traffic": None, "kernel": kernel_name,
+                    "peak_source": "FP64 tensor (DMMA) pipe: b200_probe_peak(dmma) measured live on this GPU; "
+                                   "MEASURED_PEAKS.json holds no FP64 peak",
+                    "probe_dfma_tflops": pk2 / 1e3, "probe_dmma_tflops": pk / 1e3}
+    elif kind == "gemm":
+        # 3xTF32: three tensor-core MMAs per FP32 product.  TF32 runs at half the bf16 rate, so the
+        # measured denominator is MEASURED_PEAKS bf16_tflops / 2 / 3.
+        ffma = ctx.probe_peak("ffma")
+        tc_kernel = "tcgen05" in kernel_name
+        peak = peaks["bf16_tflops"] * 1e3 / 2.0 / 3.0 if tc_kernel else ffma
+        roofline = {"bound": "tensor" if tc_kernel else "fp32-pipe", "achieved": per_gpu_gflops / 1e3,
                     "peak": peak / 1e3, "unit": "TFLOP/s", "frac": per_gpu_gflops / peak, "traffic": None,
                     "kernel": kernel_name,
-                    "peak_source": f"b200_probe_peak({probe}) measured live on this GPU; "
-                                   "MEASURED_PEAKS.json holds no FP64/FP32 pipe peak"}
-        if pk2:
-            roofline["probe_dfma_tflops"] = pk2 / 1e3
-            roofline["probe_dmma_tflops"] = pk / 1e3
+                    "peak_source": (f"bf16_tflops of {peak_src} / 2 (TF32 = half the bf16 tensor rate) / 3 "
+                                    "(3xTF32: three MMAs per FP32 product)") if tc_kernel else
+                                   "b200_probe_peak(ffma) measured live on this GPU",
+                    "probe_ffma_tflops": ffma / 1e3, "frac_of_ffma_peak": per_gpu_gflops / ffma}
     else:
         roofline = {"bound": "hbm", "achieved": per_gpu_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": per_gpu_gbs / peaks["hbm_gbs"], "traffic": None, "kernel": kernel_name,
@@ -482,8 +500,8 @@ def run_own_arm(args, kind, dtype, dim):
     line = {
         "metric": f"{'D' if dtype == 'f64' else 'S'}{kind.upper()} GFLOP/s (GPU-BLOB formula)",
         "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": dtype, "data": "synthetic", "config": workload_config(kind, dtype, dim, world),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if (args.strong and world > 1) else "weak", "vs_baseline": None,
+        "dtype": dtype, "data": "synthetic", "config": workload_config(kind, dtype, dim, world, args.strong),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "GFLOP/s", "h2d_bytes_per_step": e["h2d"],
                 "d2h_bytes_per_step": e["d2h"], "steps": e2e_steps,
@@ -512,6 +530,8 @@ def main():
     ap.add_argument("--workload", default="dgemm", choices=["dgemm", "sgemm", "dgemv", "sgemv"])
     ap.add_argument("--dim", type=int, default=0)
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--strong", action="store_true",
+                    help="N > 1: partition ONE dim^3 (dim^2) problem across the GPUs (BASELINE config 5) instead of weak scaling")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     kind = "gemm" if args.workload.endswith("gemm") else "gemv"
