@@ -315,36 +315,36 @@ def bench_e2e(blob, ctx, kind, dtype, dim, steps, warmup, barrier=lambda: None):
 
 
 def bench_e2e_multi(blob, ctx, torch, dist, kind, dtype, dim, steps, warmup, barrier, rank, world, loc):
-    """N > 1 end to end: every step the replicated operand (A for GEMM, x for GEMV) goes
-    host -> GPU 0 over PCIe and then to every GPU with an NCCL broadcast over NVLink; each
-    rank uploads its own slab (B columns / A rows), runs the kernel and downloads its slab
-    of the result (C columns / y rows) to its own pinned host buffer."""
+    """N > 1 end to end.  Every step: each rank uploads its 1/N share of the replicated
+    operand (A for GEMM, x for GEMV) over its OWN PCIe link, an NCCL all-gather over
+    NVLink replicates it on every GPU, and each rank uploads its slab (B columns / A
+    rows), runs the kernel and downloads its slab of the result (C columns / y rows) to
+    its own pinned host buffer."""
     import numpy as np
     s = ELEM[dtype]
     tdt = torch.float64 if dtype == "f64" else torch.float32
     md = blob.OFFLOAD_ONCE
     rep_count = dim * dim if kind == "gemm" else dim          # A / x
+    share = (rep_count + world - 1) // world                  # this rank's piece of it
     slab_count = dim * loc                                    # B slab / A row block
     out_count = dim * loc if kind == "gemm" else loc          # C slab / y block
-    h_rep, _d = ctx.alloc(md, rep_count * s) if rank == 0 else (None, None)
+    h_share, _d = ctx.alloc(md, share * s)
     h_slab, d_slab = ctx.alloc(md, slab_count * s)
     h_out, d_out = ctx.alloc(md, out_count * s)
-    rep_t = torch.zeros(rep_count, dtype=tdt, device="cuda")  # NCCL needs a torch tensor
+    rep_t = torch.zeros(share * world, dtype=tdt, device="cuda")   # NCCL needs torch tensors
+    share_t = torch.zeros(share, dtype=tdt, device="cuda")
     rng = np.random.default_rng(7 + rank)
-    v = blob.host_view(h_slab, slab_count, dtype)
-    for o in range(0, v.size, 1 << 24):
-        v[o:o + (1 << 24)] = rng.integers(0, 100, min(1 << 24, v.size - o)) / (3.0 if kind == "gemm" else 7.0)
-    if rank == 0:
-        vr = blob.host_view(h_rep, rep_count, dtype)
-        for o in range(0, vr.size, 1 << 24):
-            vr[o:o + (1 << 24)] = rng.integers(0, 100, min(1 << 24, vr.size - o)) / (7.0 if kind == "gemm" else 3.0)
+    for h, cnt, div in ((h_slab, slab_count, 3.0 if kind == "gemm" else 7.0),
+                        (h_share, share, 7.0 if kind == "gemm" else 3.0)):
+        v = blob.host_view(h, cnt, dtype)
+        for o in range(0, v.size, 1 << 24):
+            v[o:o + (1 << 24)] = rng.integers(0, 100, min(1 << 24, v.size - o)) / div
 
     def step():
-        if rank == 0:
-            ctx.h2d(rep_t, h_rep, rep_count * s, 0)
+        ctx.h2d(share_t, h_share, share * s, 0)
         ctx.h2d(d_slab, h_slab, slab_count * s, 1)
         ctx.sync()
-        dist.broadcast(rep_t, src=0)
+        dist.all_gather_into_tensor(rep_t, share_t)
         torch.cuda.synchronize()
         if kind == "gemm":
             ctx.gemm(dtype, dim, loc, dim, 1.0, rep_t, dim, d_slab, dim, 0.0, d_out, dim)
@@ -363,11 +363,10 @@ def bench_e2e_multi(blob, ctx, torch, dist, kind, dtype, dim, steps, warmup, bar
     barrier()
     dt = time.perf_counter() - t0
     launches = ctx.launch_count() - l0
-    if rank == 0:
-        ctx.free(md, h_rep, _d)
+    ctx.free(md, h_share, _d)
     ctx.free(md, h_slab, d_slab)
     ctx.free(md, h_out, d_out)
-    h2d = (rep_count + slab_count * world) * s   # whole job: one replicated operand + every slab
+    h2d = (share + slab_count) * world * s       # whole job: the replicated operand once + every slab
     return {"seconds": dt, "h2d": h2d, "d2h": out_count * s * world, "launches": launches}
 
 
