@@ -264,9 +264,216 @@ sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
   if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// ------------------------------------------------- CTA-pair kernel (256 x 256)
+//
+// One UMMA of M = 128, N = 128, K = 8 (TF32) lasts 64 tensor-pipe clocks and reads
+// 4 KB of A + 4 KB of B from shared memory: 128 B/clk, the whole shared-memory
+// bandwidth of an SM, before TMA has written a byte -- the single-CTA kernel above
+// stalls there (ncu: tensor pipe 74 % active).  Pairing the two SMs of a TPC
+// (tcgen05 cta_group::2) makes one UMMA M = 256, N = 256: each CTA still feeds its
+// own 128 rows of A, but only HALF of B's columns (the hardware shares B between the
+// pair), so a 128-clock UMMA reads 4 + 4 KB per SM = 64 B/clk and TMA adds 43 B/clk.
+//
+//   cluster (2,1,1), 384 threads per CTA:
+//     warp 0      TMA producer: own rows of A_hi/A_lo, own column half of B_hi/B_lo;
+//                 bytes of BOTH CTAs are counted on the LEADER's full barrier
+//     warp 1      MMA issuer (leader CTA only); tcgen05.commit multicasts the
+//                 "stage free" / "chunk ready" arrivals to both CTAs
+//     warp 2      TMEM allocator (all 512 columns: 2 accumulator stages x 256)
+//     warps 4-11  epilogue: lane quarter = warp % 4, column half = (warp - 4) / 4,
+//                 128 running sums per thread (registers moved over with setmaxnreg)
+namespace pair {
+
+constexpr int CTA_M = 128;            // rows of A and C per CTA
+constexpr int PAIR_M = 2 * CTA_M;     // UMMA M
+constexpr int PAIR_N = 256;           // UMMA N
+constexpr int CTA_N = PAIR_N / 2;     // columns of B each CTA stages
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = 128 + 32 * EPI_WARPS;
+constexpr uint32_t TMEM_COLS2 = ACC_STAGES * PAIR_N;  // 512
+constexpr uint32_t A_TILE2 = CTA_M * BK * 4;          // 16 KB
+constexpr uint32_t B_TILE2 = CTA_N * BK * 4;          // 16 KB
+constexpr uint32_t STAGE_BYTES2 = 2 * A_TILE2 + 2 * B_TILE2;
+constexpr uint32_t SMEM_BYTES2 = STAGES * STAGE_BYTES2 + 1024 + 256;
+constexpr uint32_t kIdesc2 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (0u << 16) |
+                             ((uint32_t)(PAIR_N >> 3) << 17) | ((uint32_t)(PAIR_M >> 4) << 24);
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                         const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                         int m, int n, int k, float alpha, float beta, float* __restrict__ C, long long ldc,
+                         int tiles_m, int tiles_n) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + STAGES * STAGE_BYTES2;
+  auto full_bar = [&](int s) { return bars + 8u * s; };                              // leader's is used
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };                  // one per CTA
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };              // one per CTA
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + ACC_STAGES + a); };  // leader's is used
+  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 2 * ACC_STAGES);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (k + BK - 1) / BK;
+  const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < ACC_STAGES; a++) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 2 * EPI_WARPS);  // every epilogue warp of both CTAs
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) tmem_alloc_2sm(tmem_slot, TMEM_COLS2);
+  tc_fence_before();
+  __syncwarp();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  auto tile_coords = [&](int tile, int& m0, int& n0) {
+    constexpr int GROUP = 8;
+    const int group_size = GROUP * tiles_n;
+    const int first_m = (tile / group_size) * GROUP;
+    const int gm = min(tiles_m - first_m, GROUP);
+    m0 = (first_m + (tile % group_size) % gm) * PAIR_M;
+    n0 = ((tile % group_size) / gm) * PAIR_N;
+  };
+
+  if (warp < 4) {
+    setmaxnreg_dec<48>();
+    if (warp == 0 && lane == 0) {
+      // ===================== TMA producer (both CTAs) =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+        int m0, n0;
+        tile_coords(tile, m0, n0);
+        const int my_m = m0 + (int)rank * CTA_M, my_n = n0 + (int)rank * CTA_N;
+        for (int kb = 0; kb < num_kb; kb++) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa_hi = base + stage * STAGE_BYTES2;
+          const uint32_t sa_lo = sa_hi + A_TILE2;
+          const uint32_t sb_hi = sa_lo + A_TILE2;
+          const uint32_t sb_lo = sb_hi + B_TILE2;
+          if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * STAGE_BYTES2);
+          const uint32_t lbar = mapa_shared(full_bar(stage), 0);
+#pragma unroll
+          for (int c = 0; c < CTA_M / 32; c++) {
+            tma_load_2d_2sm(sa_hi + c * 4096, &map_a_hi, lbar, my_m + c * 32, kb * BK);
+            tma_load_2d_2sm(sa_lo + c * 4096, &map_a_lo, lbar, my_m + c * 32, kb * BK);
+          }
+          tma_load_2d_2sm(sb_hi, &map_b_hi, lbar, kb * BK, my_n);
+          tma_load_2d_2sm(sb_lo, &map_b_lo, lbar, kb * BK, my_n);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+      // tail: every stage this CTA filled has been released, i.e. no UMMA still reads
+      // this CTA's shared memory and no multicast arrival is still in flight to it
+      for (int s = 0; s < STAGES; s++) {
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    } else if (warp == 1 && rank == 0 && lane == 0) {
+      // ===================== MMA issuer (leader CTA) =====================
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+        for (int kb0 = 0; kb0 < num_kb; kb0 += KB_PER_CHUNK) {
+          mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * PAIR_N;
+          const int kb1 = min(num_kb, kb0 + KB_PER_CHUNK);
+          for (int kb = kb0; kb < kb1; kb++) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t sa_hi = base + stage * STAGE_BYTES2;
+            const uint32_t sa_lo = sa_hi + A_TILE2;
+            const uint32_t sb_hi = sa_lo + A_TILE2;
+            const uint32_t sb_lo = sb_hi + B_TILE2;
+#pragma unroll
+            for (int ks = 0; ks < BK / UMMA_K; ks++) {
+              const uint64_t a_hi = umma_desc(sa_hi + ks * 1024, 4096, 512, kSwizzle128B_Base32B);
+              const uint64_t a_lo = umma_desc(sa_lo + ks * 1024, 4096, 512, kSwizzle128B_Base32B);
+              const uint64_t b_hi = umma_desc(sb_hi + ks * 32, 16, 1024, kSwizzle128B);
+              const uint64_t b_lo = umma_desc(sb_lo + ks * 32, 16, 1024, kSwizzle128B);
+              umma_tf32_2sm(d_tmem, a_lo, b_hi, kIdesc2, (kb != kb0) || (ks != 0));
+              umma_tf32_2sm(d_tmem, a_hi, b_lo, kIdesc2, 1);
+              umma_tf32_2sm(d_tmem, a_hi, b_hi, kIdesc2, 1);
+            }
+            umma_commit_2sm(empty_bar(stage), 3);  // frees this stage in both CTAs
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          umma_commit_2sm(tfull_bar(acc), 3);  // chunk complete -> both CTAs' epilogues
+          if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (both CTAs) =====================
+    setmaxnreg_inc<224>();
+    const int q = warp & 3;           // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2; // which 128 of the 256 accumulator columns
+    const uint32_t leader_tempty0 = mapa_shared(tempty_bar(0), 0);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+      int m0, n0;
+      tile_coords(tile, m0, n0);
+      float sum[CTA_N];
+#pragma unroll
+      for (int j = 0; j < CTA_N; j++) sum[j] = 0.0f;
+      for (int kb0 = 0; kb0 < num_kb; kb0 += KB_PER_CHUNK) {
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + acc * PAIR_N + half * CTA_N + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+        for (int c0 = 0; c0 < CTA_N; c0 += 32) {
+          float v[32];
+          tmem_ld32(taddr + c0, v);
+#pragma unroll
+          for (int j = 0; j < 32; j++) sum[c0 + j] += v[j];
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(leader_tempty0 + 8u * acc);
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      }
+      const int row = m0 + (int)rank * CTA_M + q * 32 + lane;
+      const int col0 = n0 + half * CTA_N;
+      if (row < m) {
+        float* cp = C + row + (long long)col0 * ldc;
+#pragma unroll
+        for (int j = 0; j < CTA_N; j++) {
+          if (col0 + j < n) {
+            const float r = alpha * sum[j];
+            cp[j * ldc] = (beta == 0.0f) ? r : r + beta * cp[j * ldc];
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncwarp();
+  cluster_sync();  // both CTAs are done with TMEM, shared memory and each other's barriers
+  if (warp == 2) tmem_dealloc_2sm(tmem_base, TMEM_COLS2);
+}
+
+}  // namespace pair
+
 // ------------------------------------------------------------------- host
 
 bool g_attr_done = false;
+bool g_pair_attr_done = false;
+int g_pair_max_clusters = 0;
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -301,17 +508,58 @@ int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const flo
   split_tf32_kernel<<<split_blocks, 256, 0, ctx->compute>>>(B, b_hi, b_lo, countB);
   B200_CUDA(cudaGetLastError());
 
+  // ---- tile config: CTA pairs on 256 x 256 tiles, or single CTAs on 128 x 128.
+  // The pair kernel does ~1/5 more work per SM-clock (shared-memory bandwidth, see its
+  // header) but quantises into fewer, larger tiles; take it when its wave efficiency
+  // keeps that advantage.
+  const long long t1m = (m + BM - 1) / BM, t1n = (n + BN - 1) / BN, tiles1 = t1m * t1n;
+  const long long t2m = (m + pair::PAIR_M - 1) / pair::PAIR_M, t2n = (n + pair::PAIR_N - 1) / pair::PAIR_N,
+                  tiles2 = t2m * t2n;
+  if (tiles1 > 0x7fffffffLL) return -1;
+  if (!g_pair_attr_done) {
+    B200_CUDA(cudaFuncSetAttribute(pair::sgemm_3xtf32_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)pair::SMEM_BYTES2));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * ctx->sm_count, 1, 1);
+    cfg.blockDim = dim3(pair::THREADS, 1, 1);
+    cfg.dynamicSmemBytes = pair::SMEM_BYTES2;
+    int clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&clusters, pair::sgemm_3xtf32_pair_kernel, &cfg) != cudaSuccess || clusters <= 0) {
+      cudaGetLastError();
+      clusters = ctx->sm_count / 2;
+    }
+    g_pair_max_clusters = std::min(clusters, ctx->sm_count / 2);
+    g_pair_attr_done = true;
+  }
+  const int pairs = g_pair_max_clusters;
+  auto wave_eff = [](long long tiles, long long slots) {
+    const long long waves = (tiles + slots - 1) / slots;
+    return (double)tiles / (double)(waves * slots);
+  };
+  // useful fraction of the tiles' area (ragged edges compute on zero fill)
+  const double fill1 = (double)m * n / ((double)t1m * BM * t1n * BN);
+  const double fill2 = (double)m * n / ((double)t2m * pair::PAIR_M * t2n * pair::PAIR_N);
+  bool use_pair = m >= pair::PAIR_M && n >= pair::PAIR_N &&
+                  1.15 * fill2 * wave_eff(tiles2, pairs) >= fill1 * wave_eff(tiles1, ctx->sm_count);
+  if (ctx->opt_sgemm_pair == 1) use_pair = true;
+  if (ctx->opt_sgemm_pair == 2) use_pair = false;
+
+  if (use_pair) {
+    const int grid = 2 * (int)std::min<long long>(tiles2, pairs);
+    pair::sgemm_3xtf32_pair_kernel<<<grid, pair::THREADS, pair::SMEM_BYTES2, ctx->compute>>>(
+        ma_hi, ma_lo, mb_hi, mb_lo, m, n, k, alpha, beta, C, (long long)ldc, (int)t2m, (int)t2n);
+    B200_CUDA(cudaGetLastError());
+    note_launch(ctx, "sgemm_3xtf32_tcgen05_pair_256x256x32", 3);
+    return 0;
+  }
   if (!g_attr_done) {
     B200_CUDA(cudaFuncSetAttribute(sgemm_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)SMEM_BYTES));
     g_attr_done = true;
   }
-  const int tiles_m = (m + BM - 1) / BM, tiles_n = (n + BN - 1) / BN;
-  const long long tiles = (long long)tiles_m * tiles_n;
-  if (tiles > 0x7fffffffLL) return -1;
-  const int grid = (int)std::min<long long>(tiles, ctx->sm_count);
+  const int grid = (int)std::min<long long>(tiles1, ctx->sm_count);
   sgemm_3xtf32_kernel<<<grid, NUM_THREADS, SMEM_BYTES, ctx->compute>>>(
-      ma_hi, ma_lo, mb_hi, mb_lo, m, n, k, alpha, beta, C, (long long)ldc, tiles_m, tiles_n);
+      ma_hi, ma_lo, mb_hi, mb_lo, m, n, k, alpha, beta, C, (long long)ldc, (int)t1m, (int)t1n);
   B200_CUDA(cudaGetLastError());
   note_launch(ctx, "sgemm_3xtf32_tcgen05_128x128x32", 3);
   return 0;

@@ -66,3 +66,56 @@ def test_sgemm_signed_inputs_absolute_error(blob, ctx, oracle):
     got, kern = run_gemm(blob, ctx, "f32", "once", m, n, k, A, B)
     assert "tcgen05" in kern, kern
     assert float(np.max(np.abs(got.astype(np.float64) - want) / bound)) <= 1e-5
+
+
+# ---- CTA-pair (cta_group::2) 256 x 256 kernel, forced ------------------------------
+PAIR_SHAPES = [
+    (256, 256, 32), (256, 256, 256), (512, 512, 96), (768, 1280, 1000), (260, 300, 200),
+    (1028, 516, 260), (2048, 2048, 32), (512, 256, 4100), (256, 256, 32768), (4096, 256, 4096),
+    (1024, 1024, 1024), (2052, 1028, 516), (300, 2304, 72), (5000, 3000, 136),
+]
+
+
+@pytest.fixture
+def force_pair(ctx):
+    ctx.set_option("sgemm_pair", "on")
+    yield
+    ctx.set_option("sgemm_pair", "auto")
+
+
+@pytest.mark.parametrize("shape", PAIR_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_sgemm_pair_kernel(blob, ctx, oracle, force_pair, shape):
+    m, n, k = shape
+    A, B, _ = oracle.init_gemm("f32", m, n, k)
+    want = oracle.harness_gemm("f32", m, n, k)
+    got, kern = run_gemm(blob, ctx, "f32", "once", m, n, k, A, B, iters=2)
+    assert "pair_256x256" in kern, kern
+    err = max_rel_err(got, want)
+    assert err <= 1e-5, (shape, kern, err)
+
+
+def test_sgemm_pair_alpha_beta_ld(blob, ctx, oracle, force_pair):
+    rng = np.random.default_rng(4)
+    m, n, k = 700, 520, 200
+    lda, ldb, ldc = 704, 200, 701
+    A = rng.random(lda * k).astype(np.float32)
+    B = rng.random(ldb * n).astype(np.float32)
+    C0 = rng.random(ldc * n).astype(np.float32)
+    want = C0.copy()
+    oracle.gemm("f32", m, n, k, 1.5, A, lda, B, ldb, 0.5, want, ldc)
+    got, kern = run_gemm(blob, ctx, "f32", "once", m, n, k, A, B, C0=C0, alpha=1.5, beta=0.5,
+                         lda=lda, ldb=ldb, ldc=ldc)
+    assert "pair_256x256" in kern, kern
+    assert max_rel_err(got, want) <= 1e-5
+
+
+def test_sgemm_pair_matches_single_cta_bitwise(blob, ctx, oracle, force_pair):
+    """Same products, same chunked accumulation order: the two tile configs must agree
+    to the last bit (a layout or barrier bug in the pair kernel would not)."""
+    m, n, k = 1024, 768, 520
+    A, B, _ = oracle.init_gemm("f32", m, n, k)
+    got2, kern2 = run_gemm(blob, ctx, "f32", "once", m, n, k, A, B)
+    ctx.set_option("sgemm_pair", "off")
+    got1, kern1 = run_gemm(blob, ctx, "f32", "once", m, n, k, A, B)
+    assert "pair" in kern2 and "128x128" in kern1, (kern1, kern2)
+    assert np.array_equal(got1, got2)
