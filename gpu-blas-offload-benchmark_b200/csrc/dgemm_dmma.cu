@@ -26,6 +26,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -256,7 +258,29 @@ dgemm_dmma_kernel(int m, int n, int k, double alpha, const double* __restrict__ 
     for (int mi = 0; mi < MI; mi++)
 #pragma unroll
       for (int ni = 0; ni < NI; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-    for (int z = 0; z < (int)gridDim.y; z++) {
+    // ZB splits per step keep >= 32 loads in flight per thread for the small configs (the
+    // 32x32 tile has only 8 accumulators per thread: one split per step is one dependent
+    // L2 round trip per split).  Ascending z order either way.
+    constexpr int EPT = MI * NI * 2;
+    constexpr int ZB = EPT >= 32 ? 1 : 32 / EPT;
+    const int nz = (int)gridDim.y;
+    int z = 0;
+    for (; ZB > 1 && z + ZB <= nz; z += ZB) {
+      double v[ZB][EPT];
+#pragma unroll
+      for (int u = 0; u < ZB; u++)
+#pragma unroll
+        for (int e = 0; e < EPT; e++) v[u][e] = __ldcg(base + (z + u) * zstride + tid + e * NTHREADS);
+#pragma unroll
+      for (int u = 0; u < ZB; u++)
+#pragma unroll
+        for (int mi = 0; mi < MI; mi++)
+#pragma unroll
+          for (int ni = 0; ni < NI; ni++)
+#pragma unroll
+            for (int r = 0; r < 2; r++) acc[mi][ni][r] += v[u][(mi * NI + ni) * 2 + r];
+    }
+    for (; z < nz; z++) {
       const double* src = base + z * zstride + tid;
 #pragma unroll
       for (int mi = 0; mi < MI; mi++)
@@ -298,6 +322,7 @@ int launch_dmma(b200_ctx* ctx, int m, int n, int k, double alpha, const double* 
     splits = (int)((min_ctas + tiles - 1) / tiles);
     const int max_splits = k / (BK * min_ktiles_per_split);
     if (splits > max_splits) splits = max_splits;
+    if (splits > 48) splits = 48;  // the last CTA's reduction is serial in the split count
     if (splits < 1) splits = 1;
   }
   int k_per_split = ((k + splits - 1) / splits + BK - 1) / BK * BK;
@@ -341,7 +366,14 @@ int dgemm_dmma_dispatch(b200_ctx* ctx, int m, int n, int k, double alpha,
   const int force = ctx->opt_dgemm_tile;  // 64 / 128 force a config (tuning)
   // measured crossover (profiles/r1_size_sweep.txt): from ~100 tiles the 128x128 TMA
   // kernel (with split-K 2 below one wave) beats the 64x64 config
-  const bool big = force ? force == 128 : t128 * 3 >= sms * 2;
+  // ... and tall-K shapes (M = N << K, e.g. 512 x 512 x 8192): few 128x128 tiles, but
+  // split-K with >= 8 k-tiles per split still fills the machine, and the big tile
+  // re-reads 4x less of A and B through L2 than 32x32 tiles do
+  const long long tallk_splits = t128 > 0 ? std::min<long long>(sms / t128, k / (8 * 32)) : 0;
+  // measured (scripts/gpu_r1k.sh): 512x512x8192 149 us vs 197 us on 32x32 tiles; at 384^2 x 6144
+  // and below the 32x32 config is still ahead
+  const bool tallk = t128 >= 16 && t128 * tallk_splits * 3 >= sms * 2;
+  const bool big = force ? force == 128 : (t128 * 3 >= sms * 2 || tallk);
 #define B200_DMMA_ARGS ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc
   if (big && aligned && ctx->opt_dgemm_tma) {
     const int rc = dgemm_tma_dispatch(B200_DMMA_ARGS);  // TMA + mbarrier pipeline (dgemm_tma.cu)

@@ -264,7 +264,9 @@ int dgemm_tma_dispatch(b200_ctx* ctx, int m, int n, int k, double alpha, const d
   if (tiles > 0x7fffffffLL) return -1;
   int splits = 1;
   if (tiles < ctx->sm_count && tiles <= ctx->num_counters) {
-    splits = (int)((ctx->sm_count + tiles - 1) / tiles);
+    // floor: tiles x splits CTAs must fit in ONE wave (ceil put 16 tiles x 10 splits = 160
+    // CTAs on 148 SMs, i.e. two waves of K/10 instead of one of K/9)
+    splits = (int)(ctx->sm_count / tiles);
     const int max_splits = k / (BK * 2);
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;

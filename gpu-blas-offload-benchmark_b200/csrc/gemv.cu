@@ -166,21 +166,33 @@ gemv_n_kernel(int m, int n, T alpha, const T* __restrict__ A, long long lda,
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  if (r < ROWS && grow < m) {
-    // fixed order, but 8 independent loads in flight per step (a plain loop is one
-    // dependent L2 round trip per split)
-    const T* src = partial + blockIdx.x * ROWS + r;
+  // All 256 threads take part: G = 256 / ROWS threads per row, thread g adds splits
+  // g, g + G, ... in ascending order with 8 independent loads in flight per step (a plain
+  // loop is one dependent L2 round trip per split), then the G partial totals of a row
+  // are added in order of g -- a fixed order, so the result is deterministic.
+  constexpr int G = kThreads / ROWS;
+  const int rr = threadIdx.x % ROWS, g = threadIdx.x / ROWS;
+  {
+    const T* src = partial + blockIdx.x * ROWS + rr;
+    const int nsplit = (int)gridDim.y;
     T total = T(0);
-    int s = 0;
-    for (; s + 8 <= (int)gridDim.y; s += 8) {
+    int s = g;
+    for (; s + 7 * G < nsplit; s += 8 * G) {
       T v[8];
 #pragma unroll
-      for (int u = 0; u < 8; u++) v[u] = __ldcg(src + (long long)(s + u) * mpad);
+      for (int u = 0; u < 8; u++) v[u] = __ldcg(src + (long long)(s + u * G) * mpad);
 #pragma unroll
       for (int u = 0; u < 8; u++) total += v[u];
     }
-    for (; s < (int)gridDim.y; s++) total += __ldcg(src + (long long)s * mpad);
-    T* yp = y + (long long)grow * incy;
+    for (; s < nsplit; s += G) total += __ldcg(src + (long long)s * mpad);
+    red[g][rr] = total;
+  }
+  __syncthreads();
+  if (g == 0 && blockIdx.x * ROWS + rr < m) {
+    T total = T(0);
+#pragma unroll
+    for (int t = 0; t < G; t++) total += red[t][rr];
+    T* yp = y + (long long)(blockIdx.x * ROWS + rr) * incy;
     *yp = (beta == T(0)) ? alpha * total : alpha * total + beta * *yp;
   }
 }
@@ -239,12 +251,14 @@ int launch_n(b200_ctx* ctx, int m, int n, T alpha, const T* A, int lda, const T*
              long long incx, T beta, T* y, long long incy, const char* name) {
   constexpr int ROWS = TX * VEC;
   const int row_blocks = (m + ROWS - 1) / ROWS;
-  // aim for ~4 resident CTAs per SM, at least 64 columns per split
+  // aim for ~4 resident CTAs per SM; a split must be wide enough for the unrolled main
+  // loop (kUnroll loads in flight per thread) to run at least once
   int splits = 1;
   const int target = ctx->sm_count * 4;
   if (row_blocks < target && row_blocks <= ctx->num_counters) {
     splits = (target + row_blocks - 1) / row_blocks;
-    const int max_splits = (n + 63) / 64;
+    constexpr int min_cols = (kUnroll * (kThreads / TX)) > 64 ? kUnroll * (kThreads / TX) : 64;
+    const int max_splits = (n + min_cols - 1) / min_cols;
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
     if (splits > 65535) splits = 65535;

@@ -80,12 +80,13 @@ constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (0
 
 // ------------------------------------------------------------------ kernels
 
-// x = hi + lo with hi = RN_tf32(x) (13 low bits zero), lo = x - hi (exact)
-__global__ void __launch_bounds__(256)
-split_tf32_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo, size_t count) {
+// x = hi + lo with hi = RN_tf32(x) (13 low bits zero), lo = x - hi (exact).  One launch
+// splits both operands: blocks [0, blocks_a) take A, the rest take B.
+__device__ __forceinline__ void split_tf32_range(const float* __restrict__ src, float* __restrict__ hi,
+                                                 float* __restrict__ lo, size_t count, int block, int blocks) {
   const size_t n4 = count / 4;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+  const size_t stride = (size_t)blocks * blockDim.x;
+  for (size_t i = (size_t)block * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 v = __ldcs(reinterpret_cast<const float4*>(src) + i);
     float4 h, l;
     h.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xFFFFE000u); l.x = v.x - h.x;
@@ -95,7 +96,7 @@ split_tf32_kernel(const float* __restrict__ src, float* __restrict__ hi, float* 
     reinterpret_cast<float4*>(hi)[i] = h;
     reinterpret_cast<float4*>(lo)[i] = l;
   }
-  if (blockIdx.x == 0 && threadIdx.x < (count & 3)) {
+  if (block == 0 && threadIdx.x < (count & 3)) {
     const size_t i = n4 * 4 + threadIdx.x;
     const float x = src[i];
     const float h = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
@@ -104,12 +105,24 @@ split_tf32_kernel(const float* __restrict__ src, float* __restrict__ hi, float* 
   }
 }
 
+__global__ void __launch_bounds__(256)
+split_tf32_kernel(const float* __restrict__ a, float* __restrict__ a_hi, float* __restrict__ a_lo, size_t count_a,
+                  const float* __restrict__ b, float* __restrict__ b_hi, float* __restrict__ b_lo, size_t count_b,
+                  int blocks_a) {
+  if ((int)blockIdx.x < blocks_a)
+    split_tf32_range(a, a_hi, a_lo, count_a, blockIdx.x, blocks_a);
+  else
+    split_tf32_range(b, b_hi, b_lo, count_b, blockIdx.x - blocks_a, gridDim.x - blocks_a);
+}
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                     const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                     int m, int n, int k, float alpha, float beta, float* __restrict__ C, long long ldc,
-                    int tiles_m, int tiles_n) {
+                    int tiles_m, int tiles_n, int splits, int kb_per_split, float* __restrict__ partial,
+                    unsigned int* __restrict__ counters) {
   extern __shared__ uint8_t smem_raw[];
+  __shared__ int s_is_last;
   // SWIZZLE_128B atoms need 1024-byte alignment
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = base + STAGES * STAGE_BYTES;
@@ -122,8 +135,13 @@ sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = tiles_m * tiles_n;
-  const int num_kb = (k + BK - 1) / BK;
+  // work item = (tile, k split): item / splits is the tile, item % splits the k range
+  const int num_items = tiles_m * tiles_n * splits;
+  const int total_kb = (k + BK - 1) / BK;
+  auto kb_range = [&](int item, int& kb_lo, int& kb_hi) {
+    kb_lo = (item % splits) * kb_per_split;
+    kb_hi = min(total_kb, kb_lo + kb_per_split);
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; s++) {
@@ -156,10 +174,11 @@ sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        int m0, n0;
-        tile_coords(tile, m0, n0);
-        for (int kb = 0; kb < num_kb; kb++) {
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        int m0, n0, kb_lo, kb_hi;
+        tile_coords(item / splits, m0, n0);
+        kb_range(item, kb_lo, kb_hi);
+        for (int kb = kb_lo; kb < kb_hi; kb++) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa_hi = base + stage * STAGE_BYTES;
           const uint32_t sa_lo = sa_hi + A_TILE;
@@ -187,12 +206,14 @@ sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     if (lane == 0) {
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        for (int kb0 = 0; kb0 < num_kb; kb0 += KB_PER_CHUNK) {
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        int kb_lo, kb_hi;
+        kb_range(item, kb_lo, kb_hi);
+        for (int kb0 = kb_lo; kb0 < kb_hi; kb0 += KB_PER_CHUNK) {
           mbar_wait(tempty_bar(acc), acc_phase ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * BN;
-          const int kb1 = min(num_kb, kb0 + KB_PER_CHUNK);
+          const int kb1 = min(kb_hi, kb0 + KB_PER_CHUNK);
           for (int kb = kb0; kb < kb1; kb++) {
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
@@ -221,15 +242,18 @@ sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int et = threadIdx.x - 128;  // 0..127 among the epilogue threads
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      int m0, n0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const int tile = item / splits;
+      int m0, n0, kb_lo, kb_hi;
       tile_coords(tile, m0, n0);
+      kb_range(item, kb_lo, kb_hi);
       float sum[BN];
 #pragma unroll
       for (int j = 0; j < BN; j++) sum[j] = 0.0f;
-      for (int kb0 = 0; kb0 < num_kb; kb0 += KB_PER_CHUNK) {
+      for (int kb0 = kb_lo; kb0 < kb_hi; kb0 += KB_PER_CHUNK) {
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
@@ -245,16 +269,67 @@ sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
         if (lane == 0) mbar_arrive(tempty_bar(acc));
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
-      const int row = m0 + q * 32 + lane;
-      if (row < m) {
-        float* cp = C + row + (long long)n0 * ldc;
+      if (splits == 1) {
+        const int row = m0 + q * 32 + lane;
+        if (row < m) {
+          float* cp = C + row + (long long)n0 * ldc;
 #pragma unroll
-        for (int j = 0; j < BN; j++) {
-          if (n0 + j < n) {
-            const float r = alpha * sum[j];
-            cp[j * ldc] = (beta == 0.0f) ? r : r + beta * cp[j * ldc];
+          for (int j = 0; j < BN; j++) {
+            if (n0 + j < n) {
+              const float r = alpha * sum[j];
+              cp[j * ldc] = (beta == 0.0f) ? r : r + beta * cp[j * ldc];
+            }
           }
         }
+        continue;
+      }
+      // ---- split-K: publish this k range's partial tile ([column][row], rows contiguous);
+      // the epilogue of whichever CTA arrives last for the tile adds the partials of all
+      // splits in ascending split order (deterministic) and writes C.
+      {
+        float* mine = partial + ((size_t)(item % splits) * (size_t)(tiles_m * tiles_n) + tile) * (BM * BN) +
+                      q * 32 + lane;
+#pragma unroll
+        for (int j = 0; j < BN; j++) __stcg(mine + j * BM, sum[j]);
+      }
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et == 0) {
+        const unsigned int prev = atomicAdd(&counters[tile], 1u);
+        const int last = (prev == (unsigned)splits - 1);
+        if (last) counters[tile] = 0;  // self-reset for the next launch
+        s_is_last = last;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const bool last = s_is_last != 0;
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone has read the flag before it is rewritten
+      if (!last) continue;
+      __threadfence();
+      // thread = 4 consecutive rows (one float4) x 32 columns: 32 independent 16-byte loads
+      // in flight per split
+      const int rg = et & 31, cg = et >> 5;
+      const float* src = partial + (size_t)tile * (BM * BN) + (size_t)(cg * 32) * BM + rg * 4;
+      const size_t zstride = (size_t)(tiles_m * tiles_n) * (BM * BN);
+      float4 tot[32];
+#pragma unroll
+      for (int j = 0; j < 32; j++) tot[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int z = 0; z < splits; z++) {
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          const float4 v = __ldcg(reinterpret_cast<const float4*>(src + z * zstride + j * BM));
+          tot[j].x += v.x; tot[j].y += v.y; tot[j].z += v.z; tot[j].w += v.w;
+        }
+      }
+      const int row0 = m0 + rg * 4;
+#pragma unroll
+      for (int j = 0; j < 32; j++) {
+        const int col = n0 + cg * 32 + j;
+        if (col >= n) continue;
+        float* cp = C + row0 + (long long)col * ldc;
+        const float r[4] = {tot[j].x, tot[j].y, tot[j].z, tot[j].w};
+#pragma unroll
+        for (int e = 0; e < 4; e++)
+          if (row0 + e < m) cp[e] = (beta == 0.0f) ? alpha * r[e] : alpha * r[e] + beta * cp[e];
       }
     }
   }
@@ -492,21 +567,37 @@ int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const flo
   const size_t offAlo = align_up(countA * 4, 1024), offBhi = 2 * offAlo;
   const size_t offBlo = offBhi + align_up(countB * 4, 1024);
   const size_t need = offBlo + align_up(countB * 4, 1024);
-  if (ensure_workspace(ctx, need)) return 1;
+  // + room for the split-K partial tiles (at most one 128 x 128 tile per SM)
+  if (ensure_workspace(ctx, need + (size_t)ctx->sm_count * BM * BN * sizeof(float))) return 1;
   char* ws = (char*)ctx->workspace;
   float *a_hi = (float*)ws, *a_lo = (float*)(ws + offAlo), *b_hi = (float*)(ws + offBhi),
         *b_lo = (float*)(ws + offBlo);
 
-  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-  if (make_tensor_map_2d(&ma_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, a_hi, m, k, (uint64_t)lda * 4, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 2;
-  if (make_tensor_map_2d(&ma_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, a_lo, m, k, (uint64_t)lda * 4, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 2;
-  if (make_tensor_map_2d(&mb_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, b_hi, k, n, (uint64_t)ldb * 4, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B)) return 2;
-  if (make_tensor_map_2d(&mb_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, b_lo, k, n, (uint64_t)ldb * 4, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B)) return 2;
+  // The four tensor maps depend only on the workspace address and the shape: ten
+  // back-to-back calls of the harness loop encode them once.
+  struct MapCache {
+    const void* ws = nullptr;
+    int m = -1, n = -1, k = -1, lda = -1, ldb = -1;
+    CUtensorMap a_hi, a_lo, b_hi, b_lo;
+  };
+  static thread_local MapCache mc;
+  if (mc.ws != ws || mc.m != m || mc.n != n || mc.k != k || mc.lda != lda || mc.ldb != ldb) {
+    mc.ws = nullptr;
+    if (make_tensor_map_2d(&mc.a_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, a_hi, m, k, (uint64_t)lda * 4, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 2;
+    if (make_tensor_map_2d(&mc.a_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, a_lo, m, k, (uint64_t)lda * 4, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 2;
+    if (make_tensor_map_2d(&mc.b_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, b_hi, k, n, (uint64_t)ldb * 4, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B)) return 2;
+    if (make_tensor_map_2d(&mc.b_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, b_lo, k, n, (uint64_t)ldb * 4, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B)) return 2;
+    mc.ws = ws; mc.m = m; mc.n = n; mc.k = k; mc.lda = lda; mc.ldb = ldb;
+  }
+  const CUtensorMap &ma_hi = mc.a_hi, &ma_lo = mc.a_lo, &mb_hi = mc.b_hi, &mb_lo = mc.b_lo;
 
-  const int split_blocks = ctx->sm_count * 8;
-  split_tf32_kernel<<<split_blocks, 256, 0, ctx->compute>>>(A, a_hi, a_lo, countA);
-  split_tf32_kernel<<<split_blocks, 256, 0, ctx->compute>>>(B, b_hi, b_lo, countB);
-  B200_CUDA(cudaGetLastError());
+  {
+    const int split_blocks = ctx->sm_count * 8;
+    int blocks_a = (int)((double)split_blocks * (double)countA / (double)(countA + countB));
+    blocks_a = std::max(1, std::min(split_blocks - 1, blocks_a));
+    split_tf32_kernel<<<split_blocks, 256, 0, ctx->compute>>>(A, a_hi, a_lo, countA, B, b_hi, b_lo, countB, blocks_a);
+    B200_CUDA(cudaGetLastError());
+  }
 
   // ---- tile config: CTA pairs on 256 x 256 tiles, or single CTAs on 128 x 128.
   // The pair kernel does ~1/5 more work per SM-clock (shared-memory bandwidth, see its
@@ -549,7 +640,7 @@ int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const flo
     pair::sgemm_3xtf32_pair_kernel<<<grid, pair::THREADS, pair::SMEM_BYTES2, ctx->compute>>>(
         ma_hi, ma_lo, mb_hi, mb_lo, m, n, k, alpha, beta, C, (long long)ldc, (int)t2m, (int)t2n);
     B200_CUDA(cudaGetLastError());
-    note_launch(ctx, "sgemm_3xtf32_tcgen05_pair_256x256x32", 3);
+    note_launch(ctx, "sgemm_3xtf32_tcgen05_pair_256x256x32", 2);
     return 0;
   }
   if (!g_attr_done) {
@@ -557,11 +648,37 @@ int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const flo
                                    (int)SMEM_BYTES));
     g_attr_done = true;
   }
-  const int grid = (int)std::min<long long>(tiles1, ctx->sm_count);
+  // split-K when the tiles alone leave most SMs idle (tall-skinny M = N << K): every
+  // split keeps >= 2 accumulation chunks, partials go through the workspace behind the
+  // operand splits
+  const int total_kb = (k + BK - 1) / BK;
+  int splits = 1;
+  if (tiles1 * 2 <= ctx->sm_count && tiles1 <= ctx->num_counters) {
+    splits = (int)(ctx->sm_count / tiles1);
+    splits = std::min(splits, std::max(1, total_kb / (2 * KB_PER_CHUNK)));
+    splits = std::min(splits, 32);
+  }
+  int kb_per_split = (total_kb + splits - 1) / splits;
+  kb_per_split = (kb_per_split + KB_PER_CHUNK - 1) / KB_PER_CHUNK * KB_PER_CHUNK;
+  splits = (total_kb + kb_per_split - 1) / kb_per_split;
+  float* partial = nullptr;
+  if (splits > 1) {
+    const size_t part_bytes = (size_t)splits * tiles1 * BM * BN * sizeof(float);
+    if (need + part_bytes > ctx->workspace_bytes) {
+      // growing the workspace would move the operand splits already queued: stay unsplit
+      // this call, grow for the next one (b200_alloc normally sized it already)
+      splits = 1;
+      kb_per_split = total_kb;
+    } else {
+      partial = (float*)(ws + need);
+    }
+  }
+  const int grid = (int)std::min<long long>(tiles1 * splits, ctx->sm_count);
   sgemm_3xtf32_kernel<<<grid, NUM_THREADS, SMEM_BYTES, ctx->compute>>>(
-      ma_hi, ma_lo, mb_hi, mb_lo, m, n, k, alpha, beta, C, (long long)ldc, (int)t1m, (int)t1n);
+      ma_hi, ma_lo, mb_hi, mb_lo, m, n, k, alpha, beta, C, (long long)ldc, (int)t1m, (int)t1n, splits,
+      kb_per_split, partial, ctx->counters);
   B200_CUDA(cudaGetLastError());
-  note_launch(ctx, "sgemm_3xtf32_tcgen05_128x128x32", 3);
+  note_launch(ctx, splits > 1 ? "sgemm_3xtf32_tcgen05_128x128x32_splitk" : "sgemm_3xtf32_tcgen05_128x128x32", 2);
   return 0;
 }
 

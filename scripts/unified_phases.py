@@ -18,9 +18,11 @@ import numpy as np  # noqa: E402
 
 dims = [int(a) for a in sys.argv[1:]] or [1024, 2048, 4096]
 reps = int(os.environ.get("REPS", "12"))
+one_lane = os.environ.get("PF_LANES", "3") == "1"   # all three prefetches on one lane instead of three
+kinds = os.environ.get("KINDS", "gemm,gemv").split(",")
 ctx = blob.Context(0)
 U = blob.OFFLOAD_UNIFIED
-for kind in ("gemm", "gemv"):
+for kind in kinds:
     for d in dims:
         cnt = (d * d, d * d, d * d) if kind == "gemm" else (d * d, d, d)
         rows = []
@@ -34,7 +36,7 @@ for kind in ("gemm", "gemv"):
             views[2][:] = 0.0
             t.append(time.perf_counter())  # cpu fill
             for lane, ((h, _), c) in enumerate(zip(ops, cnt)):
-                ctx.prefetch(h, c * 8, True, lane)
+                ctx.prefetch(h, c * 8, True, 0 if one_lane else lane)
             ctx.sync()
             t.append(time.perf_counter())  # prefetch to gpu
             for _ in range(10):
@@ -56,7 +58,7 @@ for kind in ("gemm", "gemv"):
             del views
         a = np.array(rows)
         names = ["alloc", "cpu_fill", "pf_to_gpu", "10_kernels", "pf_C_back", "cpu_read", "release"]
-        print(f"--- d{kind} {d}: ms per phase over {reps} reps (median | max | rep-of-max)  checksum {chk:.3f}")
+        print(f"--- PF_LANES={1 if one_lane else 3} d{kind} {d}: ms per phase over {reps} reps (median | max | rep-of-max)  checksum {chk:.3f}")
         for j, nm in enumerate(names):
             print(f"   {nm:11s} {np.median(a[:, j]):9.3f} | {a[:, j].max():9.3f} | {int(a[:, j].argmax())}")
         timed = a[:, 2] + a[:, 3] + a[:, 4]

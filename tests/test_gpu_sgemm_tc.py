@@ -112,10 +112,29 @@ def test_sgemm_pair_alpha_beta_ld(blob, ctx, oracle, force_pair):
 def test_sgemm_pair_matches_single_cta_bitwise(blob, ctx, oracle, force_pair):
     """Same products, same chunked accumulation order: the two tile configs must agree
     to the last bit (a layout or barrier bug in the pair kernel would not)."""
-    m, n, k = 1024, 768, 520
+    m, n, k = 2048, 1536, 264  # 192 single-CTA tiles: more than one wave, so no split-K there
     A, B, _ = oracle.init_gemm("f32", m, n, k)
     got2, kern2 = run_gemm(blob, ctx, "f32", "once", m, n, k, A, B)
     ctx.set_option("sgemm_pair", "off")
     got1, kern1 = run_gemm(blob, ctx, "f32", "once", m, n, k, A, B)
-    assert "pair" in kern2 and "128x128" in kern1, (kern1, kern2)
+    assert "pair" in kern2 and kern1.endswith("128x128x32"), (kern1, kern2)
     assert np.array_equal(got1, got2)
+
+
+@pytest.mark.parametrize("shape", [(128, 128, 8192), (512, 512, 8192), (384, 260, 4100), (200, 130, 2052)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_sgemm_tensor_core_split_k(blob, ctx, oracle, shape):
+    """Tall-skinny M = N << K: (tile, k-split) work items, partials reduced in split order by
+    the last-arriving CTA; repeated calls exercise the self-resetting arrival counters."""
+    m, n, k = shape
+    A, B, _ = oracle.init_gemm("f32", m, n, k)
+    want = oracle.harness_gemm("f32", m, n, k)
+    ctx.set_option("sgemm_pair", "off")
+    try:
+        got, kern = run_gemm(blob, ctx, "f32", "once", m, n, k, A, B, iters=3)
+        got2, _ = run_gemm(blob, ctx, "f32", "once", m, n, k, A, B, iters=1)
+    finally:
+        ctx.set_option("sgemm_pair", "auto")
+    assert "splitk" in kern, kern
+    assert max_rel_err(got, want) <= 1e-5
+    assert np.array_equal(got, got2)  # deterministic reduction order
