@@ -61,6 +61,20 @@ def gemv_bytes(m, n, s):  # include/doGemv.hh:391-395
     return (m * n + n + m) * s
 
 
+def ncu_traffic(workload, kernel_name):
+    """DRAM bytes (read + write) of ONE launch of the dominant kernel, from the committed
+    `ncu --set full` capture of this workload's bench command (profiles/r1_traffic.json,
+    written by scripts/ncu_traffic.py from the .ncu-rep); None when the capture is of a
+    different kernel than the one that just ran."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    t = json.load(open(p)).get(workload)
+    if not t or t.get("kernel_label") != kernel_name:
+        return None, None
+    return t["dram_read_bytes"] + t["dram_write_bytes"], t.get("source")
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -474,6 +488,12 @@ def run_own_arm(args, kind, dtype, dim):
                     "frac": per_gpu_gbs / peaks["hbm_gbs"], "traffic": None, "kernel": kernel_name,
                     "peak_source": f"hbm_gbs of {peak_src} (burst copy figure)"}
 
+    traffic, traffic_src = ncu_traffic(args.workload, kernel_name) if (world == 1 and dim == default_dim(kind)) else (None, None)
+    roofline["traffic"] = traffic
+    roofline["traffic_source"] = traffic_src
+    roofline["algorithmic_bytes"] = nbytes
+    roofline["algorithmic_flops"] = flops
+
     # --- the other three kernels at their headline sizes (explanatory) ------
     extras = {}
     if not args.no_extras and world == 1:
@@ -520,6 +540,10 @@ def run_own_arm(args, kind, dtype, dim):
         dist.destroy_process_group()
 
 
+def default_dim(kind):
+    return 8192 if kind == "gemm" else 32768
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -535,7 +559,7 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     kind = "gemm" if args.workload.endswith("gemm") else "gemv"
     dtype = "f64" if args.workload[0] == "d" else "f32"
-    dim = args.dim or (8192 if kind == "gemm" else 32768)
+    dim = args.dim or default_dim(kind)
     if args.impl == "reference":
         run_reference_arm(args, kind, dtype, dim)
     else:

@@ -63,6 +63,19 @@ static int lanes_wait_for_compute(b200_ctx* ctx) {
   return 0;
 }
 
+// A sweep to d = 320 walks through ~15 capacity classes per operand; with 12 cached blocks
+// the pool kept evicting (and re-creating) them, and a FRESH managed allocation costs
+// 4-7 ms in the first timed region that prefetches it (profiles/r1_unified_notes.md).
+constexpr size_t kMaxCachedBlocks = 48;
+
+// Managed blocks: power-of-two classes.  Untouched managed pages cost nothing physical, a
+// coarse class means a handful of allocations per process instead of one per size.
+static size_t round_capacity_managed(size_t bytes) {
+  size_t p = 64u << 10;
+  while (p < bytes) p *= 2;
+  return p;
+}
+
 static size_t round_capacity(size_t bytes) {
   const size_t min_gran = 64u << 10;
   if (bytes <= min_gran) return min_gran;
@@ -94,7 +107,7 @@ static void cache_put(std::vector<CachedBlock>& cache, void* p, size_t cap,
   cache.push_back({p, cap, alias});
   size_t total = 0;
   for (auto& b : cache) total += b.capacity;
-  while (cache.size() > 12 || total > max_total) {
+  while (cache.size() > kMaxCachedBlocks || total > max_total) {
     total -= cache.front().capacity;
     free_fn(cache.front().ptr);
     cache.erase(cache.begin());
@@ -261,7 +274,7 @@ int b200_alloc(b200_ctx* ctx, int mode, size_t bytes, void** host, void** dev) {
     // asynchronous UVM driver work (unmap, page-table teardown) that lands in the
     // next timed region
     if (ensure_workspace(ctx, std::min<size_t>(4 * bytes + ((size_t)32 << 20), (size_t)24 << 30))) return 1;
-    const size_t cap = round_capacity(bytes);
+    const size_t cap = round_capacity_managed(bytes);
     void* p = cache_take(ctx->managed_cache, cap);
     if (!p) B200_CUDA(cudaMallocManaged(&p, cap, cudaMemAttachGlobal));
     ctx->live_managed.push_back({p, cap});
@@ -510,7 +523,9 @@ int gemm_offload(b200_ctx* ctx, int m, int n, int k, T alpha, const T* hA, T* dA
   // ---- small problems: one shot, fewest API calls (latency matters, not overlap).
   // C is only uploaded when beta != 0 -- with beta == 0 BLAS never reads it, so the
   // reference's third upload (cuBLAS/gemm.hh:130-131) is dead traffic.
-  if (bytesA + bytesB + bytesC <= ctx->opt_zerocopy_gemm_bytes) {
+  // (C is written over PCIe in 64-byte pieces by the small-tile kernels: beyond ~112 KiB of
+  // output the one-shot path below is faster -- M=N=128..144, K=8..9: 38-44 us vs 36-40)
+  if (bytesA + bytesB + bytesC <= ctx->opt_zerocopy_gemm_bytes && bytesC <= ((size_t)112 << 10)) {
     // ---- tiny problems: zero copy.  The kernel reads A and B straight from pinned host
     // memory over PCIe and writes C back the same way: one launch + one stream sync
     // instead of two uploads, a launch, a download and a sync.

@@ -28,6 +28,8 @@
 //     special code; the only requirement is TMA's: lda, ldb even and 16-byte aligned
 //     bases (otherwise dgemm_dmma.cu's cp.async path runs).
 #include <stdio.h>
+
+#include <algorithm>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -42,7 +44,9 @@ using namespace ptx;
 constexpr int BM = 128, BN = 128, BK = 32;
 constexpr int STAGES = 3;
 constexpr int CONSUMER_WARPS = 8;
-constexpr int NTHREADS = 32 * (CONSUMER_WARPS + 1);
+// 8 consumer warps (two warpgroups) + one producer warpgroup (1 working warp, 3 idle): whole
+// warpgroups so that setmaxnreg can move the producer group's registers to the consumers
+constexpr int NTHREADS = 32 * (CONSUMER_WARPS + 4);
 constexpr uint32_t A_STAGE_BYTES = (BM / 16) * BK * 128;  // 8 chunks x [32 k][128 B]
 constexpr uint32_t B_STAGE_BYTES = (BK / 16) * BN * 128;  // 2 halves x [128 n][128 B]
 constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
@@ -81,13 +85,21 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
 
-  constexpr int GROUP = 8;
-  const int bid = blockIdx.x;
-  const int group_size = GROUP * tiles_n;
-  const int first_m = (bid / group_size) * GROUP;
-  const int gm = min(tiles_m - first_m, GROUP);
-  const int m0 = (first_m + (bid % group_size) % gm) * BM;
-  const int n0 = ((bid % group_size) / gm) * BN;
+  // Persistent over tiles when there is no split-K (gridDim.y == 1, gridDim.x <= tiles):
+  // CTA b takes tiles b, b + gridDim.x, ...; the producer runs up to STAGES k-tiles ahead
+  // ACROSS tile boundaries and the consumers' C stores drain behind the next tile's DMMAs,
+  // so a short-K tile no longer pays load latency + compute + store in sequence
+  // (M = N = 8192, K = 32: DMMA pipe 51 % active with one CTA per tile).
+  // With split-K the grid is (tiles, splits) and every CTA handles exactly one tile.
+  const int num_tiles = tiles_m * tiles_n;
+  auto tile_coords = [&](int tile, int& m0, int& n0) {
+    constexpr int GROUP = 8;
+    const int group_size = GROUP * tiles_n;
+    const int first_m = (tile / group_size) * GROUP;
+    const int gm = min(tiles_m - first_m, GROUP);
+    m0 = (first_m + (tile % group_size) % gm) * BM;
+    n0 = ((tile % group_size) / gm) * BN;
+  };
   const int kbeg = blockIdx.y * k_per_split;
   const int kend = min(k, kbeg + k_per_split);
   const int ntiles = (kend - kbeg + BK - 1) / BK;
@@ -101,57 +113,64 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   }
   __syncthreads();
 
-  if (warp == CONSUMER_WARPS) {
+  if (warp >= CONSUMER_WARPS) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    setmaxnreg_dec<40>();
+    if (warp == CONSUMER_WARPS && lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int kt = 0; kt < ntiles; kt++) {
-        mbar_wait(empty_bar(stage), phase ^ 1);
-        const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
-        const int kb = kbeg + kt * BK;
-        // A split-K slice must not read past its own k range: the zero fill only covers
-        // k >= K, so the last tile of an inner slice is clipped by the tensor map of the
-        // full matrix -- k_per_split is a multiple of BK, which makes every slice but the
-        // last end on a tile boundary.
-        mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int m0, n0;
+        tile_coords(tile, m0, n0);
+        for (int kt = 0; kt < ntiles; kt++) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+          const int kb = kbeg + kt * BK;
+          // A split-K slice must not read past its own k range: the zero fill only covers
+          // k >= K, so the last tile of an inner slice is clipped by the tensor map of the
+          // full matrix -- k_per_split is a multiple of BK, which makes every slice but the
+          // last end on a tile boundary.
+          mbar_expect_tx(full_bar(stage), STAGE_BYTES);
 #pragma unroll
-        for (int c = 0; c < BM / 16; c++) tma_load_2d(sa + c * 4096, &map_a, full_bar(stage), m0 + c * 16, kb);
+          for (int c = 0; c < BM / 16; c++) tma_load_2d(sa + c * 4096, &map_a, full_bar(stage), m0 + c * 16, kb);
 #pragma unroll
-        for (int h = 0; h < BK / 16; h++) tma_load_2d(sb + h * 16384, &map_b, full_bar(stage), kb + h * 16, n0);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          for (int h = 0; h < BK / 16; h++) tma_load_2d(sb + h * 16384, &map_b, full_bar(stage), kb + h * 16, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
       }
     }
-    // the producer warp takes no part in the epilogue, but must stay for the
-    // block-wide barriers of the split-K reduction below
+    return;  // the split-K reduction below synchronises the consumer warps only
   }
+  // 64 accumulator doubles + double-buffered fragments per thread: ~200 registers, more than
+  // the 168 a 384-thread block gets at launch
+  setmaxnreg_inc<232>();
 
   const int wm = warp & 1, wn = (warp >> 1) & 3;
   const int g = lane >> 2, t = lane & 3;
   double acc[MI][NI][2];
-#pragma unroll
-  for (int i = 0; i < MI; i++)
-#pragma unroll
-    for (int j = 0; j < NI; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  if (warp < CONSUMER_WARPS) {
-    // ===================== DMMA consumers =====================
-    // A fragment byte offsets inside a stage for (mi parity p, step s); + (mi/2)*4096 + kk*1024
-    uint32_t offA[2][2];
+  // A fragment byte offsets inside a stage for (mi parity p, step s); + (mi/2)*4096 + kk*1024
+  uint32_t offA[2][2];
 #pragma unroll
-    for (int p = 0; p < 2; p++)
+  for (int p = 0; p < 2; p++)
 #pragma unroll
-      for (int s = 0; s < 2; s++) {
-        const int x = p * 4 + (g >> 1), kq = 2 * t + s;
-        offA[p][s] = (uint32_t)(wm * 4 * 4096 + (g & 1) * 8 + kq * 128 + ((x ^ kq) << 4));
-      }
-    // B fragment byte offsets for even / odd k groups; + ni*1024 + (kk/2)*16384
-    const int rg = (g & 1) * 4 + (g >> 1);  // column of the 8-wide tile this lane group reads
-    const uint32_t offB0 = A_STAGE_BYTES + (uint32_t)((wn * 32 + rg) * 128 + ((t ^ rg) << 4));
-    const uint32_t offB1 = A_STAGE_BYTES + (uint32_t)((wn * 32 + rg) * 128 + (((4 + t) ^ rg) << 4));
+    for (int s = 0; s < 2; s++) {
+      const int x = p * 4 + (g >> 1), kq = 2 * t + s;
+      offA[p][s] = (uint32_t)(wm * 4 * 4096 + (g & 1) * 8 + kq * 128 + ((x ^ kq) << 4));
+    }
+  // B fragment byte offsets for even / odd k groups; + ni*1024 + (kk/2)*16384
+  const int rg = (g & 1) * 4 + (g >> 1);  // column of the 8-wide tile this lane group reads
+  const uint32_t offB0 = A_STAGE_BYTES + (uint32_t)((wn * 32 + rg) * 128 + ((t ^ rg) << 4));
+  const uint32_t offB1 = A_STAGE_BYTES + (uint32_t)((wn * 32 + rg) * 128 + (((4 + t) ^ rg) << 4));
 
-    int stage = 0;
-    uint32_t phase = 0;
+  int stage = 0;
+  uint32_t phase = 0;
+  // ===================== DMMA consumers: all k-tiles of one output tile =====================
+  auto run_tile = [&]() {
+#pragma unroll
+    for (int i = 0; i < MI; i++)
+#pragma unroll
+      for (int j = 0; j < NI; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
     for (int kt = 0; kt < ntiles; kt++) {
       mbar_wait(full_bar(stage), phase);
       const uint32_t sbase = base + stage * STAGE_BYTES;
@@ -187,14 +206,49 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       if (lane == 0) mbar_arrive(empty_bar(stage));
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
+  };
+  // epilogue: DMMA column (2t + r) of tile ni is matrix column r*4 + t (the B permutation)
+  auto store_tile = [&](int m0, int n0) {
+#pragma unroll
+    for (int ni = 0; ni < NI; ni++) {
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        const int gj = n0 + wn * 32 + ni * 8 + r * 4 + t;
+        if (gj >= n) continue;
+#pragma unroll
+        for (int mi = 0; mi < MI; mi++) {
+          const int gi = m0 + wm * 64 + mi * 8 + g;
+          if (gi >= m) continue;
+          double* cp = C + gi + gj * ldc;
+          const double v = alpha * acc[mi][ni][r];
+          *cp = (beta == 0.0) ? v : v + beta * *cp;
+        }
+      }
+    }
+  };
+
+  if (gridDim.y == 1) {
+    // ---- persistent
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int m0, n0;
+      tile_coords(tile, m0, n0);
+      run_tile();
+      store_tile(m0, n0);
+    }
+    return;
   }
 
-  if (gridDim.y > 1) {
-    // split-K: consumers publish fragment-ordered partials, the last CTA of the tile sums them
+  // ---- split-K: one tile per CTA; consumers publish fragment-ordered partials, the last
+  // CTA of the tile sums them
+  const int bid = blockIdx.x;
+  int m0, n0;
+  tile_coords(bid, m0, n0);
+  run_tile();
+  {
     constexpr int CT = 32 * CONSUMER_WARPS;
     const long long tile_elems = (long long)BM * BN;
     const long long zstride = (long long)gridDim.x * tile_elems;
-    if (warp < CONSUMER_WARPS) {
+    {
       double* mine = partial + (long long)blockIdx.y * zstride + (long long)bid * tile_elems;
 #pragma unroll
       for (int mi = 0; mi < MI; mi++)
@@ -204,16 +258,16 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           for (int r = 0; r < 2; r++) mine[((mi * NI + ni) * 2 + r) * CT + tid] = acc[mi][ni][r];
     }
     __threadfence();
-    __syncthreads();
+    asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 consumer warps
     if (tid == 0) {
       const unsigned int prev = atomicAdd(&counters[bid], 1u);
       is_last = (prev == gridDim.y - 1);
       if (is_last) counters[bid] = 0;
     }
-    __syncthreads();
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     if (!is_last) return;
     __threadfence();
-    if (warp < CONSUMER_WARPS) {
+    {
       const double* src0 = partial + (long long)bid * tile_elems + tid;
 #pragma unroll
       for (int mi = 0; mi < MI; mi++)
@@ -230,25 +284,7 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
     }
   }
-
-  if (warp >= CONSUMER_WARPS) return;
-  // epilogue: DMMA column (2t + r) of tile ni is matrix column r*4 + t (the B permutation)
-#pragma unroll
-  for (int ni = 0; ni < NI; ni++) {
-#pragma unroll
-    for (int r = 0; r < 2; r++) {
-      const int gj = n0 + wn * 32 + ni * 8 + r * 4 + t;
-      if (gj >= n) continue;
-#pragma unroll
-      for (int mi = 0; mi < MI; mi++) {
-        const int gi = m0 + wm * 64 + mi * 8 + g;
-        if (gi >= m) continue;
-        double* cp = C + gi + gj * ldc;
-        const double v = alpha * acc[mi][ni][r];
-        *cp = (beta == 0.0) ? v : v + beta * *cp;
-      }
-    }
-  }
+  store_tile(m0, n0);
 }
 
 bool g_attr_done = false;
@@ -290,7 +326,8 @@ int dgemm_tma_dispatch(b200_ctx* ctx, int m, int n, int k, double alpha, const d
     B200_CUDA(cudaFuncSetAttribute(dgemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     g_attr_done = true;
   }
-  dim3 grid((unsigned)tiles, splits);
+  // no split-K: persistent CTAs, one per SM, each walks tiles b, b + grid, ...
+  dim3 grid((unsigned)(splits > 1 ? tiles : std::min<long long>(tiles, ctx->sm_count)), splits);
   dgemm_tma_kernel<<<grid, NTHREADS, SMEM_BYTES, ctx->compute>>>(map_a, map_b, m, n, k, alpha, beta, C,
                                                                  (long long)ldc, tiles_m, tiles_n, k_per_split,
                                                                  partial, ctx->counters);

@@ -104,8 +104,13 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// Arrive on a peer CTA's mbarrier.  Default semantics (.release at CTA scope) on purpose:
+// .release.cluster compiles to MEMBAR.ALL.GPU, which makes the arriving thread wait for
+// every global store it has in flight (ncu: the epilogue's C stores of the previous tile
+// drained before each arrive, 2 TB/s instead of 5.5).  What the arrive must order here are
+// the thread's tcgen05.ld reads, and tcgen05.wait::ld + fence::before_thread_sync do that.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load into THIS CTA's shared memory whose bytes are counted on the LEADER's mbarrier
 __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar,
