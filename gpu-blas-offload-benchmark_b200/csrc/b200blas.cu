@@ -188,6 +188,7 @@ int b200_ctx_create(b200_ctx** out, int device) {
   if (const char* e = getenv("B200_ZEROCOPY_GEMV_BYTES")) ctx->opt_zerocopy_gemv_bytes = (size_t)atoll(e);
   if (const char* e = getenv("B200_DGEMM_MIN")) ctx->opt_dgemm_min = atoi(e);
   if (const char* e = getenv("B200_DGEMM_TMA")) ctx->opt_dgemm_tma = strcmp(e, "off") != 0 && strcmp(e, "0") != 0;
+  if (const char* e = getenv("B200_DGEMM_STREAMK")) ctx->opt_dgemm_streamk = strcmp(e, "off") != 0 && strcmp(e, "0") != 0;
   if (const char* e = getenv("B200_DGEMM_TILE")) ctx->opt_dgemm_tile = (atoi(e) == 32 || atoi(e) == 64 || atoi(e) == 128) ? atoi(e) : 0;
   ctx->num_counters = 1 << 16;
   B200_CUDA(cudaMalloc((void**)&ctx->counters, ctx->num_counters * sizeof(unsigned int)));
@@ -246,6 +247,12 @@ int b200_ctx_set_option(b200_ctx* ctx, const char* key, const char* value) {
     else if (!strcmp(value, "64")) ctx->opt_dgemm_tile = 64;
     else if (!strcmp(value, "128")) ctx->opt_dgemm_tile = 128;
     else B200_REQUIRE(false, "b200_ctx_set_option: dgemm_tile must be auto|32|64|128, got '%s'", value);
+    return 0;
+  }
+  if (!strcmp(key, "dgemm_streamk")) {
+    if (!strcmp(value, "on") || !strcmp(value, "auto")) ctx->opt_dgemm_streamk = 1;
+    else if (!strcmp(value, "off")) ctx->opt_dgemm_streamk = 0;
+    else B200_REQUIRE(false, "b200_ctx_set_option: dgemm_streamk must be on|off, got '%s'", value);
     return 0;
   }
   if (!strcmp(key, "dgemm_tma")) {

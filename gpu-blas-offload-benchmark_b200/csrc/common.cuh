@@ -80,6 +80,7 @@ struct b200_ctx {
   size_t opt_zerocopy_gemm_bytes = 200u << 10;
   size_t opt_zerocopy_gemv_bytes = 16u << 20;
   int opt_dgemm_min = 32;  // smallest m, n the DMMA kernels take (one 32x32 tile; below: DFMA SIMT path)
+  int opt_dgemm_streamk = 1;  // 1: stream-K over the partial last wave of the TMA kernel, 0: whole tiles only
   int opt_dgemm_tma = 1;   // 1: large aligned DGEMMs use the TMA-fed kernel, 0: cp.async kernel
 
   const char* last_kernel = "none";

@@ -31,6 +31,7 @@
 
 #include <algorithm>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 dgemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  int m, int n, int k, double alpha, double beta, double* __restrict__ C, long long ldc,
                  int tiles_m, int tiles_n, int k_per_split, double* __restrict__ partial,
-                 unsigned int* __restrict__ counters) {
+                 unsigned int* __restrict__ counters, int sk_tiles, int sk_slots) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = base + STAGES * STAGE_BYTES;
@@ -104,6 +105,20 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const int kend = min(k, kbeg + k_per_split);
   const int ntiles = (kend - kbeg + BK - 1) / BK;
 
+  // Stream-K for the partial last wave (persistent mode only).  The first
+  // dp_tiles = num_tiles - sk_tiles tiles are whole-tile work, round-robin; the k-tiles of
+  // the remaining sk_tiles tiles form one linear space of sk_tiles * ntiles units that is
+  // cut into gridDim.x equal contiguous segments, so every SM gets the same amount of the
+  // leftover work instead of `sk_tiles` SMs getting a whole tile and the rest nothing
+  // (2048^3: 256 tiles on 148 SMs = 2 tile-times -> 1.73).  A segment that does not cover
+  // its whole tile publishes a partial; the last contributor to arrive adds the partials in
+  // contributor order (fixed by the segment arithmetic, not by timing) and stores C.
+  const int dp_tiles = num_tiles - sk_tiles;
+  const long long sk_units = (long long)sk_tiles * ntiles;
+  auto sk_begin = [&](int b) { return (long long)b * sk_units / (int)gridDim.x; };
+  // the CTA whose segment contains unit u: max b with sk_begin(b) <= u
+  auto sk_cta_of = [&](long long u) { return (int)(((u + 1) * (int)gridDim.x - 1) / sk_units); };
+
   if (tid == 0) {
     for (int s = 0; s < STAGES; s++) {
       mbar_init(full_bar(s), 1);
@@ -119,6 +134,34 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (warp == CONSUMER_WARPS && lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      auto load_ktile = [&](int m0, int n0, int kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        const uint32_t sa = base + stage * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+        mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+#pragma unroll
+        for (int c = 0; c < BM / 16; c++) tma_load_2d(sa + c * 4096, &map_a, full_bar(stage), m0 + c * 16, kb);
+#pragma unroll
+        for (int h = 0; h < BK / 16; h++) tma_load_2d(sb + h * 16384, &map_b, full_bar(stage), kb + h * 16, n0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      };
+      if (sk_tiles > 0) {
+        for (int tile = blockIdx.x; tile < dp_tiles; tile += gridDim.x) {
+          int m0, n0;
+          tile_coords(tile, m0, n0);
+          for (int kt = 0; kt < ntiles; kt++) load_ktile(m0, n0, kt * BK);
+        }
+        long long u = sk_begin(blockIdx.x);
+        const long long uend = sk_begin(blockIdx.x + 1);
+        while (u < uend) {
+          const int t = (int)(u / ntiles), kt0 = (int)(u % ntiles);
+          const int kt1 = (int)min((long long)ntiles, kt0 + (uend - u));
+          int m0, n0;
+          tile_coords(dp_tiles + t, m0, n0);
+          for (int kt = kt0; kt < kt1; kt++) load_ktile(m0, n0, kt * BK);
+          u += kt1 - kt0;
+        }
+        return;
+      }
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int m0, n0;
         tile_coords(tile, m0, n0);
@@ -166,12 +209,12 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   int stage = 0;
   uint32_t phase = 0;
   // ===================== DMMA consumers: all k-tiles of one output tile =====================
-  auto run_tile = [&]() {
+  auto run_tile = [&](int nkt) {
 #pragma unroll
     for (int i = 0; i < MI; i++)
 #pragma unroll
       for (int j = 0; j < NI; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-    for (int kt = 0; kt < ntiles; kt++) {
+    for (int kt = 0; kt < nkt; kt++) {
       mbar_wait(full_bar(stage), phase);
       const uint32_t sbase = base + stage * STAGE_BYTES;
       // register double buffering over the 8 DMMA steps (kk = 0..3, s = 0..1) of the tile
@@ -227,12 +270,68 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
   };
 
+  constexpr int CT = 32 * CONSUMER_WARPS;
+  constexpr long long tile_elems = (long long)BM * BN;
   if (gridDim.y == 1) {
-    // ---- persistent
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    // ---- persistent: whole tiles ...
+    for (int tile = blockIdx.x; tile < dp_tiles; tile += gridDim.x) {
       int m0, n0;
       tile_coords(tile, m0, n0);
-      run_tile();
+      run_tile(ntiles);
+      store_tile(m0, n0);
+    }
+    if (sk_tiles == 0) return;
+    // ---- ... then this CTA's segment of the stream-K space
+    long long u = sk_begin(blockIdx.x);
+    const long long uend = sk_begin(blockIdx.x + 1);
+    while (u < uend) {
+      const int t = (int)(u / ntiles), kt0 = (int)(u % ntiles);
+      const int kt1 = (int)min((long long)ntiles, kt0 + (uend - u));
+      int m0, n0;
+      tile_coords(dp_tiles + t, m0, n0);
+      run_tile(kt1 - kt0);
+      u += kt1 - kt0;
+      if (kt0 == 0 && kt1 == ntiles) {  // the segment happens to cover the whole tile
+        store_tile(m0, n0);
+        continue;
+      }
+      const int first = sk_cta_of((long long)t * ntiles);
+      const int ncontrib = sk_cta_of((long long)(t + 1) * ntiles - 1) - first + 1;
+      double* slots = partial + (long long)t * sk_slots * tile_elems;
+      {
+        double* mine = slots + (long long)((int)blockIdx.x - first) * tile_elems;
+#pragma unroll
+        for (int mi = 0; mi < MI; mi++)
+#pragma unroll
+          for (int ni = 0; ni < NI; ni++)
+#pragma unroll
+            for (int r = 0; r < 2; r++) __stcg(mine + ((mi * NI + ni) * 2 + r) * CT + tid, acc[mi][ni][r]);
+      }
+      __threadfence();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (tid == 0) {
+        const unsigned int prev = atomicAdd(&counters[t], 1u);
+        is_last = (prev == (unsigned)ncontrib - 1);
+        if (is_last) counters[t] = 0;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const bool last = is_last;
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // flag read by all before the next segment rewrites it
+      if (!last) continue;
+      __threadfence();
+#pragma unroll
+      for (int mi = 0; mi < MI; mi++)
+#pragma unroll
+        for (int ni = 0; ni < NI; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+      for (int z = 0; z < ncontrib; z++) {
+        const double* src = slots + (long long)z * tile_elems + tid;
+#pragma unroll
+        for (int mi = 0; mi < MI; mi++)
+#pragma unroll
+          for (int ni = 0; ni < NI; ni++)
+#pragma unroll
+            for (int r = 0; r < 2; r++) acc[mi][ni][r] += __ldcg(src + ((mi * NI + ni) * 2 + r) * CT);
+      }
       store_tile(m0, n0);
     }
     return;
@@ -243,10 +342,8 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const int bid = blockIdx.x;
   int m0, n0;
   tile_coords(bid, m0, n0);
-  run_tile();
+  run_tile(ntiles);
   {
-    constexpr int CT = 32 * CONSUMER_WARPS;
-    const long long tile_elems = (long long)BM * BN;
     const long long zstride = (long long)gridDim.x * tile_elems;
     {
       double* mine = partial + (long long)blockIdx.y * zstride + (long long)bid * tile_elems;
@@ -315,6 +412,23 @@ int dgemm_tma_dispatch(b200_ctx* ctx, int m, int n, int k, double alpha, const d
     if (ensure_workspace(ctx, (size_t)splits * tiles * BM * BN * sizeof(double))) return 1;
     partial = (double*)ctx->workspace;
   }
+  // stream-K over the partial last wave (see the kernel): worth it when that wave leaves
+  // >= 10 % of the SMs idle, every SM's segment is >= 4 k-tiles and the whole job is short
+  // enough for the saving to show (<= 8 waves)
+  int sk_tiles = 0, sk_slots = 0;
+  const int P = ctx->sm_count;
+  const int ktiles = (k + BK - 1) / BK;
+  if (splits == 1 && tiles > P / 2 && ctx->opt_dgemm_streamk) {
+    const int rem = (int)(tiles % P);
+    const long long waves = (tiles + P - 1) / P;
+    const long long seg = (long long)rem * ktiles / P;  // k-tiles per SM in the stream-K space
+    if (rem > 0 && rem * 10 <= P * 9 && seg >= 4 && waves <= 8 && rem <= ctx->num_counters) {
+      sk_tiles = rem;
+      sk_slots = (int)(ktiles / seg) + 2;  // upper bound on contributors per tile
+      if (ensure_workspace(ctx, (size_t)sk_tiles * sk_slots * BM * BN * sizeof(double))) return 1;
+      partial = (double*)ctx->workspace;
+    }
+  }
   CUtensorMap map_a, map_b;
   if (make_tensor_map_2d(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, A, m, k, (uint64_t)lda * 8, 16, BK,
                          CU_TENSOR_MAP_SWIZZLE_128B))
@@ -327,12 +441,13 @@ int dgemm_tma_dispatch(b200_ctx* ctx, int m, int n, int k, double alpha, const d
     g_attr_done = true;
   }
   // no split-K: persistent CTAs, one per SM, each walks tiles b, b + grid, ...
-  dim3 grid((unsigned)(splits > 1 ? tiles : std::min<long long>(tiles, ctx->sm_count)), splits);
+  dim3 grid((unsigned)(splits > 1 ? tiles : (sk_tiles ? P : std::min<long long>(tiles, P))), splits);
   dgemm_tma_kernel<<<grid, NTHREADS, SMEM_BYTES, ctx->compute>>>(map_a, map_b, m, n, k, alpha, beta, C,
                                                                  (long long)ldc, tiles_m, tiles_n, k_per_split,
-                                                                 partial, ctx->counters);
+                                                                 partial, ctx->counters, sk_tiles, sk_slots);
   B200_CUDA(cudaGetLastError());
-  note_launch(ctx, splits > 1 ? "dgemm_dmma_tma_128x128x32_splitk" : "dgemm_dmma_tma_128x128x32");
+  note_launch(ctx, splits > 1 ? "dgemm_dmma_tma_128x128x32_splitk"
+                          : (sk_tiles ? "dgemm_dmma_tma_128x128x32_streamk" : "dgemm_dmma_tma_128x128x32"));
   return 0;
 }
 

@@ -62,8 +62,10 @@ int b200_ctx_device(const b200_ctx* ctx, int* device, int* sm_count);
  *   "sgemm"      = "auto" | "tc" (force tcgen05 3xTF32) | "ffma" (force the FP32-pipe path)
  *   "dgemm_tile" = "auto" | "32" | "64" | "128"
  *   "dgemm_tma"  = "on" | "off"   (large aligned DGEMM: TMA-fed kernel vs cp.async kernel)
- * Defaults come from the environment at context creation: B200_SGEMM, B200_DGEMM_TILE,
- * B200_DGEMM_TMA. */
+ *   "dgemm_streamk" = "on" | "off" (TMA kernel: stream-K over the partial last wave of tiles)
+ *   "sgemm_pair" = "auto" | "on" | "off" (tcgen05 SGEMM: CTA-pair 256x256 tiles vs single-CTA 128x128)
+ * Defaults come from the environment at context creation: B200_SGEMM, B200_SGEMM_PAIR,
+ * B200_DGEMM_TILE, B200_DGEMM_TMA, B200_DGEMM_STREAMK. */
 int b200_ctx_set_option(b200_ctx* ctx, const char* key, const char* value);
 
 /* ---- memory -------------------------------------------------------------
