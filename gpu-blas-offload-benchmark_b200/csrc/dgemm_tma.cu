@@ -252,6 +252,21 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   };
   // epilogue: DMMA column (2t + r) of tile ni is matrix column r*4 + t (the B permutation)
   auto store_tile = [&](int m0, int n0) {
+    if (beta == 0.0 && m0 + BM <= m && n0 + BN <= n) {
+      // interior tile, the harness' case: one address per column, 8 stores at immediate
+      // offsets -- the general path below spends ~10 instructions per element on guards and
+      // 64-bit address arithmetic, which shows when K is short (M = N = 8192, K = 32)
+#pragma unroll
+      for (int ni = 0; ni < NI; ni++) {
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+          double* col = C + (m0 + wm * 64 + g) + (long long)(n0 + wn * 32 + ni * 8 + r * 4 + t) * ldc;
+#pragma unroll
+          for (int mi = 0; mi < MI; mi++) col[mi * 8] = alpha * acc[mi][ni][r];
+        }
+      }
+      return;
+    }
 #pragma unroll
     for (int ni = 0; ni < NI; ni++) {
 #pragma unroll

@@ -115,6 +115,29 @@ split_tf32_kernel(const float* __restrict__ a, float* __restrict__ a_hi, float* 
     split_tf32_range(b, b_hi, b_lo, count_b, blockIdx.x - blocks_a, gridDim.x - blocks_a);
 }
 
+// Store one thread's row of `NCOL` column results: C[row, col0 + j] = alpha * sum[j] (+ beta * C).
+// The per-column work is kept to a multiply, an address step and the store: guards and the
+// beta test are hoisted (ncu on M = N = 8192, K = 32: the epilogue warps were issue-latency
+// bound on ~19 instructions per column).
+template <int NCOL>
+__device__ __forceinline__ void store_row(float* __restrict__ cp, long long ldc, const float (&sum)[NCOL],
+                                          int ncols, float alpha, float beta) {
+  if (ncols <= 0) return;
+  if (beta == 0.0f) {
+#pragma unroll
+    for (int j = 0; j < NCOL; j++) {
+      if (j < ncols) *cp = alpha * sum[j];  // predicated store, no branch
+      cp += ldc;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < NCOL; j++) {
+      if (j < ncols) *cp = alpha * sum[j] + beta * *cp;
+      cp += ldc;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                     const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -271,16 +294,7 @@ sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
       }
       if (splits == 1) {
         const int row = m0 + q * 32 + lane;
-        if (row < m) {
-          float* cp = C + row + (long long)n0 * ldc;
-#pragma unroll
-          for (int j = 0; j < BN; j++) {
-            if (n0 + j < n) {
-              const float r = alpha * sum[j];
-              cp[j * ldc] = (beta == 0.0f) ? r : r + beta * cp[j * ldc];
-            }
-          }
-        }
+        if (row < m) store_row<BN>(C + row + (long long)n0 * ldc, ldc, sum, n - n0, alpha, beta);
         continue;
       }
       // ---- split-K: publish this k range's partial tile ([column][row], rows contiguous);
@@ -493,6 +507,8 @@ sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
     }
   } else {
     // ===================== epilogue (both CTAs) =====================
+    // 128 x 48 + 256 x 224 = 63488 of the SM's 65536 registers.  (232 would be an exact fit on
+    // paper; on hardware the TRY_ALLOC never succeeded and the kernel hung -- keep slack.)
     setmaxnreg_inc<224>();
     const int q = warp & 3;           // TMEM lane quarter this warp may access
     const int half = (warp - 4) >> 2; // which 128 of the 256 accumulator columns
@@ -523,16 +539,7 @@ sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
       }
       const int row = m0 + (int)rank * CTA_M + q * 32 + lane;
       const int col0 = n0 + half * CTA_N;
-      if (row < m) {
-        float* cp = C + row + (long long)col0 * ldc;
-#pragma unroll
-        for (int j = 0; j < CTA_N; j++) {
-          if (col0 + j < n) {
-            const float r = alpha * sum[j];
-            cp[j * ldc] = (beta == 0.0f) ? r : r + beta * cp[j * ldc];
-          }
-        }
-      }
+      if (row < m) store_row<CTA_N>(C + row + (long long)col0 * ldc, ldc, sum, n - col0, alpha, beta);
     }
   }
 
