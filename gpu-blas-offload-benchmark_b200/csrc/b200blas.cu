@@ -583,12 +583,15 @@ int gemm_offload(b200_ctx* ctx, int m, int n, int k, T alpha, const T* hA, T* dA
   };
   mark(ctx->lane[0], "start", 0, 0);
   const double flops = 2.0 * m * n * (double)k;
-  const double rate = sizeof(T) == 8 ? 30e12 : ((lda % 4 == 0 && ldb % 4 == 0) ? 180e12 : 40e12);
+  const double rate = sizeof(T) == 8 ? 34e12 : ((lda % 4 == 0 && ldb % 4 == 0) ? 270e12 : 40e12);
   const bool compute_bound = flops / rate > (double)(bytesA + bytesB) / 50e9;
-  int nk = compute_bound ? std::max(1, std::min(4, k / 1024)) : 1;
+  // compute-bound: up to 8 x 8 pieces -- the first block starts after 2 of 16 pieces are up
+  // (2.4 ms of a 19.4 ms upload at 8192^3) and only the last slab's download (1/8 of C) is
+  // exposed at the end; 1024-wide blocks still run at ~0.95 of the big-GEMM rate (stream-K)
+  int nk = compute_bound ? std::max(1, std::min(8, k / 1024)) : 1;
   int kc = ((k + nk - 1) / nk + 31) / 32 * 32;
   nk = (k + kc - 1) / kc;
-  int ns = std::max(1, std::min(compute_bound ? 4 : 8, n / 256));
+  int ns = std::max(1, std::min(8, compute_bound ? n / 1024 : n / 256));
   int cols = ((n + ns - 1) / ns + 127) / 128 * 128;
   ns = (n + cols - 1) / cols;
   constexpr int kMax = 8;
