@@ -524,8 +524,12 @@ def run_own_arm(args, kind, dtype, dim):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "GFLOP/s", "h2d_bytes_per_step": e["h2d"],
                 "d2h_bytes_per_step": e["d2h"], "steps": e2e_steps,
-                "path": "b200_%sgem%s_offload (Always mode of gpu::gem%s_gpu<T>), pinned host buffers"
-                        % ("d" if dtype == "f64" else "s", "m" if kind == "gemm" else "v", "m" if kind == "gemm" else "v")},
+                "path": ("b200_%sgem%s_offload (Always mode of gpu::gem%s_gpu<T>), pinned host buffers"
+                         % ("d" if dtype == "f64" else "s", "m" if kind == "gemm" else "v", "m" if kind == "gemm" else "v"))
+                if world == 1 else
+                ("per rank and step: b200_h2d_async of its 1/N share of the replicated operand + its slab from "
+                 "pinned host buffers, NCCL all-gather over NVLink, b200_%sgem%s, b200_d2h_async of its result slab"
+                 % ("d" if dtype == "f64" else "s", "m" if kind == "gemm" else "v"))},
         "gpu_launches": launches,
         "roofline": roofline,
         "cpu_baseline": {"value": cpu["value"], "unit": "GFLOP/s", "cores": cpu["cores"], "kind": cpu["kind"],
