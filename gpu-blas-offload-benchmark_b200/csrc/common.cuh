@@ -89,6 +89,9 @@ struct b200_ctx {
 
 namespace b200 {
 
+// cudaFuncSetAttribute is per device: one-time flags are kept per device id
+constexpr int kMaxDevices = 64;
+
 int ensure_workspace(b200_ctx* ctx, size_t bytes);
 // Make the compute stream wait for every copy lane that has pending uploads.
 int join_lanes_into_compute(b200_ctx* ctx);

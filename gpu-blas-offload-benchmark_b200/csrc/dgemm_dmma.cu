@@ -335,7 +335,8 @@ int launch_dmma(b200_ctx* ctx, int m, int n, int k, double alpha, const double* 
   }
   constexpr size_t SMEM = smem_bytes<BM, BN>();
   auto kern = dgemm_dmma_kernel<ALIGNED, BM, BN, WM, WN>;
-  static bool attr_set = false;
+  static bool attr_set_dev[kMaxDevices] = {};
+  bool& attr_set = attr_set_dev[ctx->device % kMaxDevices];
   if (!attr_set) {
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     attr_set = true;

@@ -391,7 +391,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                          const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                          int m, int n, int k, float alpha, float beta, float* __restrict__ C, long long ldc,
-                         int tiles_m, int tiles_n) {
+                         int tiles_m, int tiles_n, int raster_group) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = base + STAGES * STAGE_BYTES2;
@@ -428,7 +428,7 @@ sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   auto tile_coords = [&](int tile, int& m0, int& n0) {
-    constexpr int GROUP = 8;
+    const int GROUP = raster_group;
     const int group_size = GROUP * tiles_n;
     const int first_m = (tile / group_size) * GROUP;
     const int gm = min(tiles_m - first_m, GROUP);
@@ -553,9 +553,9 @@ sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
 
 // ------------------------------------------------------------------- host
 
-bool g_attr_done = false;
-bool g_pair_attr_done = false;
-int g_pair_max_clusters = 0;
+bool g_attr_done_dev[kMaxDevices] = {};
+bool g_pair_attr_done_dev[kMaxDevices] = {};
+int g_pair_max_clusters_dev[kMaxDevices] = {};
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -614,6 +614,8 @@ int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const flo
   const long long t2m = (m + pair::PAIR_M - 1) / pair::PAIR_M, t2n = (n + pair::PAIR_N - 1) / pair::PAIR_N,
                   tiles2 = t2m * t2n;
   if (tiles1 > 0x7fffffffLL) return -1;
+  bool& g_pair_attr_done = g_pair_attr_done_dev[ctx->device % kMaxDevices];
+  int& g_pair_max_clusters = g_pair_max_clusters_dev[ctx->device % kMaxDevices];
   if (!g_pair_attr_done) {
     B200_CUDA(cudaFuncSetAttribute(pair::sgemm_3xtf32_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)pair::SMEM_BYTES2));
@@ -643,13 +645,16 @@ int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const flo
   if (ctx->opt_sgemm_pair == 2) use_pair = false;
 
   if (use_pair) {
+    static const char* rg_env = getenv("B200_SGEMM_RASTER");  // tuning: m-tiles per raster group
+    const int raster_group = rg_env ? std::max(1, atoi(rg_env)) : 8;
     const int grid = 2 * (int)std::min<long long>(tiles2, pairs);
     pair::sgemm_3xtf32_pair_kernel<<<grid, pair::THREADS, pair::SMEM_BYTES2, ctx->compute>>>(
-        ma_hi, ma_lo, mb_hi, mb_lo, m, n, k, alpha, beta, C, (long long)ldc, (int)t2m, (int)t2n);
+        ma_hi, ma_lo, mb_hi, mb_lo, m, n, k, alpha, beta, C, (long long)ldc, (int)t2m, (int)t2n, raster_group);
     B200_CUDA(cudaGetLastError());
     note_launch(ctx, "sgemm_3xtf32_tcgen05_pair_256x256x32", 2);
     return 0;
   }
+  bool& g_attr_done = g_attr_done_dev[ctx->device % kMaxDevices];
   if (!g_attr_done) {
     B200_CUDA(cudaFuncSetAttribute(sgemm_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)SMEM_BYTES));

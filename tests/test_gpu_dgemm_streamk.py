@@ -53,3 +53,32 @@ def test_dgemm_streamk(blob, ctx, oracle, shape):
         oracle.gemm("f64", bs, bs, k, 1.0, a_cm, bs, b_cm, k, 0.0, want, bs)
         got = np.ascontiguousarray(Ch[j0:j0 + bs, i0:i0 + bs]).reshape(-1)
         assert max_rel_err(got, want) <= 1e-12, (shape, kern, (i0, j0))
+
+
+@pytest.mark.parametrize("shape,expect", [((1700, 1650, 1100), "streamk"), ((512, 512, 8192), "splitk"),
+                                          ((2048, 2048, 96), "128x128x32")],
+                         ids=["streamk", "splitk", "persistent"])
+def test_dgemm_tma_alpha_beta(blob, ctx, oracle, shape, expect):
+    """alpha / beta through every schedule of the TMA kernel: C = 1.5 A B - 0.25 C0, checked on
+    sampled blocks against the oracle (the accumulate blocks of the Always-mode pipeline use
+    beta = 1 on exactly these paths)."""
+    import torch
+    m, n, k = shape
+    A = _fill(torch, m * k, 21, 7.0)
+    B = _fill(torch, k * n, 22, 3.0)
+    C0 = _fill(torch, m * n, 23, 11.0)
+    C = C0.clone()
+    ctx.gemm("f64", m, n, k, 1.5, A, m, B, k, -0.25, C, m)
+    ctx.sync()
+    kern = ctx.last_kernel()
+    assert kern.endswith(expect), kern
+    Ah, Bh, Ch, C0h = A.view(k, m).cpu().numpy(), B.view(n, k).cpu().numpy(), C.view(n, m).cpu().numpy(), \
+        C0.view(n, m).cpu().numpy()
+    bs = 36
+    for (i0, j0) in ((0, 0), (m - bs, n - bs), (m // 2, n // 3), (130, n - bs)):
+        a_cm = np.ascontiguousarray(Ah[:, i0:i0 + bs]).reshape(-1)
+        b_cm = np.ascontiguousarray(Bh[j0:j0 + bs, :]).reshape(-1)
+        want = np.ascontiguousarray(C0h[j0:j0 + bs, i0:i0 + bs]).reshape(-1).copy()
+        oracle.gemm("f64", bs, bs, k, 1.5, a_cm, bs, b_cm, k, -0.25, want, bs)
+        got = np.ascontiguousarray(Ch[j0:j0 + bs, i0:i0 + bs]).reshape(-1)
+        assert max_rel_err(got, want) <= 1e-12, (shape, kern, (i0, j0))

@@ -138,3 +138,25 @@ def test_sgemm_tensor_core_split_k(blob, ctx, oracle, shape):
     assert "splitk" in kern, kern
     assert max_rel_err(got, want) <= 1e-5
     assert np.array_equal(got, got2)  # deterministic reduction order
+
+
+def test_sgemm_split_k_alpha_beta(blob, ctx, oracle):
+    """beta != 0 through the split-K reduction epilogue (applied once, by the last arriver)."""
+    rng = np.random.default_rng(6)
+    m, n, k = 200, 136, 4104
+    lda, ldb, ldc = 200, 4104, 203
+    A = rng.random(lda * k).astype(np.float32)
+    B = rng.random(ldb * n).astype(np.float32)
+    C0 = (rng.random(ldc * n) * 1000).astype(np.float32)
+    want = C0.copy()
+    oracle.gemm("f32", m, n, k, 0.75, A, lda, B, ldb, 2.0, want, ldc)
+    ctx.set_option("sgemm_pair", "off")
+    try:
+        got, kern = run_gemm(blob, ctx, "f32", "once", m, n, k, A, B, C0=C0, alpha=0.75, beta=2.0,
+                             lda=lda, ldb=ldb, ldc=ldc, iters=1)
+    finally:
+        ctx.set_option("sgemm_pair", "auto")
+    assert "splitk" in kern, kern
+    g, w = got.reshape(n, ldc), want.reshape(n, ldc)
+    assert np.array_equal(g[:, m:], C0.reshape(n, ldc)[:, m:])  # padding rows untouched
+    assert max_rel_err(g[:, :m].ravel(), w[:, :m].ravel()) <= 1e-5
