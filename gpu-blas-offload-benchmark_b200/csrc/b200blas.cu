@@ -639,6 +639,8 @@ int gemm_offload(b200_ctx* ctx, int m, int n, int k, T alpha, const T* hA, T* dA
   struct Block { int c, j; bool issued; };
   Block blocks[kMax * kMax];
   int nb = 0, order[kMax * kMax];
+  double start_time[kMax * kMax];
+  bool mergeable[kMax * kMax] = {};
   for (int j = 0; j < ns; j++)
     for (int c = 0; c < nk; c++) blocks[nb++] = {c, j, false};
   {
@@ -657,6 +659,7 @@ int gemm_offload(b200_ctx* ctx, int m, int n, int k, T alpha, const T* hA, T* dA
     }
     double now = 0.0;
     for (int i = 0; i < nb; i++) {
+      start_time[i] = 0.0;
       int best = -1;
       double best_ready = 0.0;
       for (int b = 0; b < nb; b++) {
@@ -667,29 +670,46 @@ int gemm_offload(b200_ctx* ctx, int m, int n, int k, T alpha, const T* hA, T* dA
       }
       const Block& bl = blocks[best];
       const int kk = std::min(kc, k - bl.c * kc), nc = std::min(cols, n - bl.j * cols);
-      now = std::max(now, std::max(arriveA[bl.c], arriveB[bl.j])) + 2.0 * m * nc * (double)kk / rate;
+      start_time[i] = std::max(now, std::max(arriveA[bl.c], arriveB[bl.j]));
+      now = start_time[i] + 2.0 * m * nc * (double)kk / rate;
       blocks[best].issued = true;
       order[i] = best;
     }
+    // A run of consecutive K-chunks of one slab whose operands are all up before the run
+    // starts is ONE GEMM over the joined K range (the late slabs of a compute-bound problem:
+    // one 8192 x 1024 x 8192 call instead of eight x1024 accumulate blocks -- longer k loops,
+    // one pass over C).  mergeable[i] = block order[i] continues the run of order[i-1].
+    for (int i = 1; i < nb; i++) {
+      const Block &p = blocks[order[i - 1]], &q = blocks[order[i]];
+      int first = i - 1;
+      while (first > 0 && mergeable[first]) first--;
+      mergeable[i] = q.j == p.j && q.c == p.c + 1 && arriveA[q.c] <= start_time[first] &&
+                     arriveB[q.j] <= start_time[first];
+    }
   }
   int done_in_slab[kMax] = {};
-  for (int i = 0; i < nb; i++) {
-    const int c = blocks[order[i]].c, j = blocks[order[i]].j;
-    const int k0 = c * kc, kk = std::min(kc, k - k0);
+  for (int i = 0; i < nb;) {
+    int last = i;  // blocks order[i..last] form one GEMM call
+    while (last + 1 < nb && mergeable[last + 1]) last++;
+    const int c0 = blocks[order[i]].c, c1 = blocks[order[last]].c, j = blocks[order[i]].j;
+    const int k0 = c0 * kc, kk = std::min(k, (c1 + 1) * kc) - k0;
     const int j0 = j * cols, nc = std::min(cols, n - j0);
-    if (!waitedA[c]) { B200_CUDA(cudaStreamWaitEvent(ctx->compute, evA[c], 0)); waitedA[c] = true; }
+    for (int c = c0; c <= c1; c++)
+      if (!waitedA[c]) { B200_CUDA(cudaStreamWaitEvent(ctx->compute, evA[c], 0)); waitedA[c] = true; }
     if (!waitedB[j]) { B200_CUDA(cudaStreamWaitEvent(ctx->compute, evB[j], 0)); waitedB[j] = true; }
     if (gemm(ctx, 0, 0, m, nc, kk, alpha, dA + (size_t)k0 * lda, lda, dB + k0 + (size_t)j0 * ldb, ldb,
              done_in_slab[j] == 0 ? beta : T(1), dC + (size_t)j0 * ldc, ldc))
       return 1;
-    mark(ctx->compute, "gemm A%d B%d", c, j);
-    if (++done_in_slab[j] == nk) {
+    mark(ctx->compute, c0 == c1 ? "gemm A%d B%d" : "gemm A%d.. B%d", c0, j);
+    done_in_slab[j] += c1 - c0 + 1;
+    if (done_in_slab[j] == nk) {
       if (record_on(ctx, ctx->compute, &ev)) return 1;
       B200_CUDA(cudaStreamWaitEvent(down, ev, 0));
       B200_CUDA(cudaMemcpyAsync(hC + (size_t)j0 * ldc, dC + (size_t)j0 * ldc, s * ((size_t)ldc * (nc - 1) + m),
                                 cudaMemcpyDeviceToHost, down));
       mark(down, "down C%d", j, 0);
     }
+    i = last + 1;
   }
   ctx->compute_unordered = false;  // every kernel above is already ordered before its download
   for (int l = 0; l < B200_NUM_LANES; l++) ctx->lane_dirty[l] = true;
