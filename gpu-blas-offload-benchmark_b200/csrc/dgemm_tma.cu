@@ -3,12 +3,18 @@
 // 128-byte-swizzled shared memory.  sm_100a only.
 //
 // Same math and tile shape as dgemm_dmma.cu (128x128x32 CTA tile, 8 consumer warps as
-// 2(M) x 4(N), 64x32 warp tiles); what changes is who moves the data:
-//   * warp 8 is the producer: one lane issues cp.async.bulk.tensor.2d for the whole
-//     stage (8 boxes of A, 2 of B, 64 KB) and arms the stage's `full` mbarrier with the
-//     byte count.  The consumer warps execute no copy instructions at all -- in the
-//     cp.async kernel their LDGSTS bursts competed with the fragment LDS for the LSU
-//     (profiles/r1_ncu_summary.md: 87% DMMA-pipe utilisation).
+// 2(M) x 4(N), 64x32 warp tiles); what changes is who moves the data and how work is scheduled:
+//   * 384 threads = 3 warpgroups.  Warpgroup 2 is the producer: one lane of its first warp
+//     issues cp.async.bulk.tensor.2d for the whole stage (8 boxes of A, 2 of B, 64 KB) and arms
+//     the stage's `full` mbarrier with the byte count; the group hands its registers to the
+//     consumers (setmaxnreg.dec 40 / .inc 232 -- a 384-thread block gets 168 at launch, the 64
+//     accumulator doubles + double-buffered fragments need ~200).  The consumer warps execute
+//     no copy instructions at all -- in the cp.async kernel their LDGSTS bursts competed with
+//     the fragment LDS for the LSU (87% DMMA-pipe utilisation there, 99% here).
+//   * persistent CTAs (one per SM) walk the tiles; the producer runs up to 3 k-tiles ahead
+//     across tile boundaries and C stores drain behind the next tile's DMMAs.  The partial last
+//     wave is scheduled stream-K (equal k-tile segments per SM, partial tiles combined by the
+//     last contributor in contributor order); fewer tiles than SMs -> split-K, grid (tiles, splits).
 //   * there is no __syncthreads in the main loop: a consumer warp waits on full[s],
 //     runs its 256 DMMAs, and one lane arrives on empty[s] (count 8); warps drift
 //     apart freely, so one warp's fragment loads hide behind another's DMMAs.

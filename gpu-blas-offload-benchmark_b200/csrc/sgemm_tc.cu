@@ -33,11 +33,16 @@
 //       thread t row t: a warp's store of one column is 32 consecutive floats
 //       of column-major C -- coalesced with no shared-memory staging.
 //
-// Structure: persistent CTAs (one per SM), 256 threads:
-//   warp 0  TMA producer      warp 1  MMA issuer (one elected lane)
-//   warp 2  TMEM allocator    warps 4-7  epilogue (TMEM -> registers -> C)
-// 3 smem stages x {A_hi, A_lo, B_hi, B_lo} 16 KB tiles, 2 TMEM accumulator
-// stages (2 x 128 columns) so the epilogue of tile i overlaps the MMAs of i+1.
+// Two kernels share the layouts above:
+//   sgemm_3xtf32_pair_kernel  CTA pairs (cta_group::2), UMMA 256x256x8 -- the large-problem
+//                             kernel, described at its definition below
+//   sgemm_3xtf32_kernel       single CTA, UMMA 128x128x8, persistent over (tile, k-split) work
+//                             items, 256 threads:
+//     warp 0  TMA producer      warp 1  MMA issuer (one elected lane)
+//     warp 2  TMEM allocator    warps 4-7  epilogue (TMEM -> registers -> C, or -> split-K
+//                                          partial + last-arriver reduction)
+//   3 smem stages x {A_hi, A_lo, B_hi, B_lo} 16 KB tiles, 2 TMEM accumulator stages so the
+//   epilogue of chunk i overlaps the MMAs of chunk i+1.
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
