@@ -456,7 +456,8 @@ int dgemm_tma_dispatch(b200_ctx* ctx, int m, int n, int k, double alpha, const d
     partial = (double*)ctx->workspace;
   }
   // stream-K over the partial last wave (see the kernel): worth it when that wave leaves
-  // >= 10 % of the SMs idle, every SM's segment is >= 4 k-tiles and the whole job is short
+  // >= 10 % of the SMs idle, every SM's segment is >= 8 k-tiles (measured: with 2-3 k-tile segments the
+  // partial-tile traffic costs more than the idle SMs, 51 vs 43 us at 2048 x 2048 x 128) and the whole job is short
   // enough for the saving to show (<= 8 waves)
   int sk_tiles = 0, sk_slots = 0;
   const int P = ctx->sm_count;
@@ -465,7 +466,7 @@ int dgemm_tma_dispatch(b200_ctx* ctx, int m, int n, int k, double alpha, const d
     const int rem = (int)(tiles % P);
     const long long waves = (tiles + P - 1) / P;
     const long long seg = (long long)rem * ktiles / P;  // k-tiles per SM in the stream-K space
-    if (rem > 0 && rem * 10 <= P * 9 && seg >= 4 && waves <= 8 && rem <= ctx->num_counters) {
+    if (rem > 0 && rem * 10 <= P * 9 && seg >= 8 && waves <= 8 && rem <= ctx->num_counters) {
       sk_tiles = rem;
       sk_slots = (int)(ktiles / seg) + 2;  // upper bound on contributors per tile
       if (ensure_workspace(ctx, (size_t)sk_tiles * sk_slots * BM * BN * sizeof(double))) return 1;

@@ -29,7 +29,7 @@ def _streamk_plan(tiles, ktiles, P):
         return 0, 0
     rem, waves = tiles % P, -(-tiles // P)
     seg = rem * ktiles // P
-    if rem > 0 and rem * 10 <= P * 9 and seg >= 4 and waves <= 8:
+    if rem > 0 and rem * 10 <= P * 9 and seg >= 8 and waves <= 8:
         return rem, ktiles // seg + 2
     return 0, 0
 
