@@ -374,7 +374,10 @@ int dgemm_dmma_dispatch(b200_ctx* ctx, int m, int n, int k, double alpha,
   // measured (scripts/gpu_r1k.sh): 512x512x8192 149 us vs 197 us on 32x32 tiles; at 384^2 x 6144
   // and below the 32x32 config is still ahead
   const bool tallk = t128 >= 16 && t128 * tallk_splits * 3 >= sms * 2;
-  const bool big = force ? force == 128 : (t128 * 3 >= sms * 2 || tallk);
+  // ... and anything from ~50 tiles whose k-tiles the stream-K schedule can spread evenly over the SMs
+  // (81 tiles at 1088^3: 105 us on 32x32 tiles, 91 us stream-K)
+  const bool streamk_fill = ctx->opt_dgemm_streamk && t128 >= 48 && t128 * (long long)(k / 32) / sms >= 8;
+  const bool big = force ? force == 128 : (t128 * 3 >= sms * 2 || tallk || streamk_fill);
 #define B200_DMMA_ARGS ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc
   if (big && aligned && ctx->opt_dgemm_tma) {
     const int rc = dgemm_tma_dispatch(B200_DMMA_ARGS);  // TMA + mbarrier pipeline (dgemm_tma.cu)

@@ -447,6 +447,12 @@ int dgemm_tma_dispatch(b200_ctx* ctx, int m, int n, int k, double alpha, const d
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
   }
+  // Split-K fills tiles x splits of the SMs; when that leaves > 10 % idle (e.g. 64 tiles x 2 on 148
+  // SMs) the stream-K schedule below -- every SM an equal share of ALL k-tiles -- is the better
+  // one-wave split, provided its segments are long enough.
+  if (splits >= 2 && ctx->opt_dgemm_streamk && tiles * splits * 10 < (long long)ctx->sm_count * 9 &&
+      tiles * ((k + BK - 1) / BK) / ctx->sm_count >= 8)
+    splits = 1;
   int k_per_split = ((k + splits - 1) / splits + BK - 1) / BK * BK;
   splits = (k + k_per_split - 1) / k_per_split;
   if (splits > 65535) return -1;
@@ -462,7 +468,7 @@ int dgemm_tma_dispatch(b200_ctx* ctx, int m, int n, int k, double alpha, const d
   int sk_tiles = 0, sk_slots = 0;
   const int P = ctx->sm_count;
   const int ktiles = (k + BK - 1) / BK;
-  if (splits == 1 && tiles > P / 2 && ctx->opt_dgemm_streamk) {
+  if (splits == 1 && ctx->opt_dgemm_streamk) {
     const int rem = (int)(tiles % P);
     const long long waves = (tiles + P - 1) / P;
     const long long seg = (long long)rem * ktiles / P;  // k-tiles per SM in the stream-K space

@@ -25,8 +25,6 @@ def _load(path, name):
 # ---------------------------------------------------------------- stream-K arithmetic
 def _streamk_plan(tiles, ktiles, P):
     """Mirror of dgemm_tma_dispatch's decision (csrc/dgemm_tma.cu)."""
-    if tiles <= P // 2:
-        return 0, 0
     rem, waves = tiles % P, -(-tiles // P)
     seg = rem * ktiles // P
     if rem > 0 and rem * 10 <= P * 9 and seg >= 8 and waves <= 8:
@@ -35,7 +33,7 @@ def _streamk_plan(tiles, ktiles, P):
 
 
 @pytest.mark.parametrize("tiles,ktiles", [(256, 64), (256, 16), (182, 35), (255, 129), (100, 64), (149, 40),
-                                          (1183, 9), (300, 1000), (75, 8)])
+                                          (1183, 9), (300, 1000), (75, 8), (64, 32), (50, 40), (36, 64)])
 def test_streamk_segments_cover_every_ktile_once(tiles, ktiles):
     P = 148
     sk_tiles, sk_slots = _streamk_plan(tiles, ktiles, P)
