@@ -579,8 +579,45 @@ int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const flo
   const size_t offAlo = align_up(countA * 4, 1024), offBhi = 2 * offAlo;
   const size_t offBlo = offBhi + align_up(countB * 4, 1024);
   const size_t need = offBlo + align_up(countB * 4, 1024);
-  // + room for the split-K partial tiles (at most one 128 x 128 tile per SM)
-  if (ensure_workspace(ctx, need + (size_t)ctx->sm_count * BM * BN * sizeof(float))) return 1;
+  // ---- schedule: CTA pairs on 256 x 256 tiles, or single CTAs on 128 x 128 tiles cut into
+  // `splits` k ranges.  Both are persistent, so time = waves x time per work item; the cost
+  // model below is in tensor-pipe clocks per k-block of 32 (pair UMMA 256x256x8: 128 clk x 12 =
+  // 1536, pipe ~99 % busy; single-CTA 128x128x8: 64 clk x 12 = 768 at ~74 % => ~1040) plus a
+  // per-item term for the exposed part of the epilogue / split-K fix-up.  It reproduces the
+  // measured crossovers (profiles/r1_size_sweep.txt: pair from 1792^3, single CTA at 1536^3,
+  // split-K 2 at 1024^3).
+  const long long t1m = (m + BM - 1) / BM, t1n = (n + BN - 1) / BN, tiles1 = t1m * t1n;
+  const long long t2m = (m + pair::PAIR_M - 1) / pair::PAIR_M, t2n = (n + pair::PAIR_N - 1) / pair::PAIR_N,
+                  tiles2 = t2m * t2n;
+  if (tiles1 > 0x7fffffffLL) return -1;
+  const int total_kb = (k + BK - 1) / BK;
+  const int P = ctx->sm_count;
+  auto waves = [](long long items, long long slots) { return (items + slots - 1) / slots; };
+  int splits = 1;
+  double cost1 = 0.0;
+  {
+    double best = -1.0;
+    const int max_s = (tiles1 <= ctx->num_counters) ? std::min(32, std::max(1, total_kb / (2 * KB_PER_CHUNK))) : 1;
+    for (int sp = 1; sp <= max_s; sp++) {
+      int kbs = (total_kb + sp - 1) / sp;
+      kbs = (kbs + KB_PER_CHUNK - 1) / KB_PER_CHUNK * KB_PER_CHUNK;
+      const int real = (total_kb + kbs - 1) / kbs;  // splits after rounding to whole chunks
+      if (real != sp && sp != 1) continue;
+      // measured: split-K over more than one wave of work items loses (2304^3, 3 splits: 188 vs 154 us)
+      if (real > 1 && tiles1 * real > P) continue;
+      const double c = (double)waves(tiles1 * real, P) * (kbs * 1040.0 + (real > 1 ? 2500.0 : 1500.0));
+      if (best < 0 || c < best * 0.97) {  // prefer fewer splits unless the gain is real
+        best = c;
+        splits = real;
+      }
+    }
+    cost1 = best;
+  }
+  int kb_per_split = (total_kb + splits - 1) / splits;
+  kb_per_split = (kb_per_split + KB_PER_CHUNK - 1) / KB_PER_CHUNK * KB_PER_CHUNK;
+  splits = (total_kb + kb_per_split - 1) / kb_per_split;
+  const size_t part_bytes = splits > 1 ? (size_t)splits * tiles1 * BM * BN * sizeof(float) : 0;
+  if (ensure_workspace(ctx, need + part_bytes)) return 1;
   char* ws = (char*)ctx->workspace;
   float *a_hi = (float*)ws, *a_lo = (float*)(ws + offAlo), *b_hi = (float*)(ws + offBhi),
         *b_lo = (float*)(ws + offBlo);
@@ -611,14 +648,6 @@ int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const flo
     B200_CUDA(cudaGetLastError());
   }
 
-  // ---- tile config: CTA pairs on 256 x 256 tiles, or single CTAs on 128 x 128.
-  // The pair kernel does ~1/5 more work per SM-clock (shared-memory bandwidth, see its
-  // header) but quantises into fewer, larger tiles; take it when its wave efficiency
-  // keeps that advantage.
-  const long long t1m = (m + BM - 1) / BM, t1n = (n + BN - 1) / BN, tiles1 = t1m * t1n;
-  const long long t2m = (m + pair::PAIR_M - 1) / pair::PAIR_M, t2n = (n + pair::PAIR_N - 1) / pair::PAIR_N,
-                  tiles2 = t2m * t2n;
-  if (tiles1 > 0x7fffffffLL) return -1;
   bool& g_pair_attr_done = g_pair_attr_done_dev[ctx->device % kMaxDevices];
   int& g_pair_max_clusters = g_pair_max_clusters_dev[ctx->device % kMaxDevices];
   if (!g_pair_attr_done) {
@@ -637,15 +666,8 @@ int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const flo
     g_pair_attr_done = true;
   }
   const int pairs = g_pair_max_clusters;
-  auto wave_eff = [](long long tiles, long long slots) {
-    const long long waves = (tiles + slots - 1) / slots;
-    return (double)tiles / (double)(waves * slots);
-  };
-  // useful fraction of the tiles' area (ragged edges compute on zero fill)
-  const double fill1 = (double)m * n / ((double)t1m * BM * t1n * BN);
-  const double fill2 = (double)m * n / ((double)t2m * pair::PAIR_M * t2n * pair::PAIR_N);
-  bool use_pair = m >= pair::PAIR_M && n >= pair::PAIR_N &&
-                  1.15 * fill2 * wave_eff(tiles2, pairs) >= fill1 * wave_eff(tiles1, ctx->sm_count);
+  const double cost2 = (double)waves(tiles2, pairs) * (total_kb * 1536.0 + 2500.0);
+  bool use_pair = m >= pair::PAIR_M && n >= pair::PAIR_N && cost2 <= cost1;
   if (ctx->opt_sgemm_pair == 1) use_pair = true;
   if (ctx->opt_sgemm_pair == 2) use_pair = false;
 
@@ -665,31 +687,7 @@ int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const flo
                                    (int)SMEM_BYTES));
     g_attr_done = true;
   }
-  // split-K when the tiles alone leave most SMs idle (tall-skinny M = N << K): every
-  // split keeps >= 2 accumulation chunks, partials go through the workspace behind the
-  // operand splits
-  const int total_kb = (k + BK - 1) / BK;
-  int splits = 1;
-  if (tiles1 * 2 <= ctx->sm_count && tiles1 <= ctx->num_counters) {
-    splits = (int)(ctx->sm_count / tiles1);
-    splits = std::min(splits, std::max(1, total_kb / (2 * KB_PER_CHUNK)));
-    splits = std::min(splits, 32);
-  }
-  int kb_per_split = (total_kb + splits - 1) / splits;
-  kb_per_split = (kb_per_split + KB_PER_CHUNK - 1) / KB_PER_CHUNK * KB_PER_CHUNK;
-  splits = (total_kb + kb_per_split - 1) / kb_per_split;
-  float* partial = nullptr;
-  if (splits > 1) {
-    const size_t part_bytes = (size_t)splits * tiles1 * BM * BN * sizeof(float);
-    if (need + part_bytes > ctx->workspace_bytes) {
-      // growing the workspace would move the operand splits already queued: stay unsplit
-      // this call, grow for the next one (b200_alloc normally sized it already)
-      splits = 1;
-      kb_per_split = total_kb;
-    } else {
-      partial = (float*)(ws + need);
-    }
-  }
+  float* partial = splits > 1 ? (float*)(ws + need) : nullptr;
   const int grid = (int)std::min<long long>(tiles1 * splits, ctx->sm_count);
   sgemm_3xtf32_kernel<<<grid, NUM_THREADS, SMEM_BYTES, ctx->compute>>>(
       ma_hi, ma_lo, mb_hi, mb_lo, m, n, k, alpha, beta, C, (long long)ldc, (int)t1m, (int)t1n, splits,
