@@ -183,6 +183,7 @@ int b200_ctx_create(b200_ctx** out, int device) {
   B200_CUDA(cudaEventCreate(&ctx->t0));
   B200_CUDA(cudaEventCreate(&ctx->t1));
   if (const char* e = getenv("B200_SGEMM")) ctx->opt_sgemm = !strcmp(e, "tc") ? 1 : !strcmp(e, "ffma") ? 2 : 0;
+  if (const char* e = getenv("B200_SGEMM_STREAMK")) ctx->opt_sgemm_streamk = strcmp(e, "off") != 0 && strcmp(e, "0") != 0;
   if (const char* e = getenv("B200_SGEMM_PAIR")) ctx->opt_sgemm_pair = !strcmp(e, "on") ? 1 : !strcmp(e, "off") ? 2 : 0;
   if (const char* e = getenv("B200_ZEROCOPY_GEMM_BYTES")) ctx->opt_zerocopy_gemm_bytes = (size_t)atoll(e);
   if (const char* e = getenv("B200_ZEROCOPY_GEMV_BYTES")) ctx->opt_zerocopy_gemv_bytes = (size_t)atoll(e);
@@ -232,6 +233,12 @@ int b200_ctx_set_option(b200_ctx* ctx, const char* key, const char* value) {
     else if (!strcmp(value, "tc")) ctx->opt_sgemm = 1;
     else if (!strcmp(value, "ffma")) ctx->opt_sgemm = 2;
     else B200_REQUIRE(false, "b200_ctx_set_option: sgemm must be auto|tc|ffma, got '%s'", value);
+    return 0;
+  }
+  if (!strcmp(key, "sgemm_streamk")) {
+    if (!strcmp(value, "on") || !strcmp(value, "auto")) ctx->opt_sgemm_streamk = 1;
+    else if (!strcmp(value, "off")) ctx->opt_sgemm_streamk = 0;
+    else B200_REQUIRE(false, "b200_ctx_set_option: sgemm_streamk must be on|off, got '%s'", value);
     return 0;
   }
   if (!strcmp(key, "sgemm_pair")) {

@@ -72,6 +72,7 @@ struct b200_ctx {
 
   // kernel-selection knobs (b200_ctx_set_option)
   int opt_sgemm = 0;       // 0 auto, 1 tc, 2 ffma
+  int opt_sgemm_streamk = 1;  // CTA-pair SGEMM kernel: 1 stream-K over the partial last wave, 0 whole tiles only
   int opt_sgemm_pair = 0;  // tcgen05 SGEMM tile config: 0 auto, 1 CTA-pair 256x256, 2 single-CTA 128x128
   int opt_dgemm_tile = 0;  // 0 auto, 64, 128
   // Always mode: operand sets up to these sizes are computed in place from pinned host

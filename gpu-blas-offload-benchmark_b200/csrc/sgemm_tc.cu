@@ -396,8 +396,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                          const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                          int m, int n, int k, float alpha, float beta, float* __restrict__ C, long long ldc,
-                         int tiles_m, int tiles_n, int raster_group) {
+                         int tiles_m, int tiles_n, int raster_group, int sk_tiles, int sk_slots,
+                         float* __restrict__ partial, unsigned int* __restrict__ counters) {
   extern __shared__ uint8_t smem_raw[];
+  __shared__ int s_is_last;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = base + STAGES * STAGE_BYTES2;
   auto full_bar = [&](int s) { return bars + 8u * s; };                              // leader's is used
@@ -413,6 +415,42 @@ sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = (k + BK - 1) / BK;
   const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  // ---- work items.  Whole tiles first (tile = pair_id, pair_id + num_pairs, ... below dp_tiles);
+  // then, if the tile count leaves a partial last wave, this pair's segment of the stream-K space:
+  // the accumulation chunks (K = 128) of the last sk_tiles tiles, cut into num_pairs equal
+  // contiguous runs (same scheme as the DGEMM kernel, csrc/dgemm_tma.cu).  A run that does not
+  // cover its whole tile publishes a partial tile; the last CTA to arrive for the tile adds the
+  // partials in contributor order and stores C.
+  const int chunks = (num_kb + KB_PER_CHUNK - 1) / KB_PER_CHUNK;
+  const int dp_tiles = num_tiles - sk_tiles;
+  const long long sk_units = (long long)sk_tiles * chunks;
+  auto sk_begin = [&](int p) { return (long long)p * sk_units / num_pairs; };
+  auto sk_pair_of = [&](long long u) { return (int)(((u + 1) * num_pairs - 1) / sk_units); };
+  struct Item { int tile, c0, c1; };
+  // iterate: call with it = -1 first; returns false when this pair has no more work
+  long long sk_u = 0, sk_end = 0;
+  int dp_next = pair_id;
+  bool sk_started = false;
+  auto next_item = [&](Item& w) -> bool {
+    if (dp_next < dp_tiles) {
+      w = {dp_next, 0, chunks};
+      dp_next += num_pairs;
+      return true;
+    }
+    if (sk_tiles == 0) return false;
+    if (!sk_started) {
+      sk_u = sk_begin(pair_id);
+      sk_end = sk_begin(pair_id + 1);
+      sk_started = true;
+    }
+    if (sk_u >= sk_end) return false;
+    const int t = (int)(sk_u / chunks), c0 = (int)(sk_u % chunks);
+    const int c1 = (int)min((long long)chunks, c0 + (sk_end - sk_u));
+    w = {dp_tiles + t, c0, c1};
+    sk_u += c1 - c0;
+    return true;
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; s++) {
@@ -447,11 +485,13 @@ sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
       // ===================== TMA producer (both CTAs) =====================
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+      Item w;
+      while (next_item(w)) {
         int m0, n0;
-        tile_coords(tile, m0, n0);
+        tile_coords(w.tile, m0, n0);
         const int my_m = m0 + (int)rank * CTA_M, my_n = n0 + (int)rank * CTA_N;
-        for (int kb = 0; kb < num_kb; kb++) {
+        const int kb_hi = min(num_kb, w.c1 * KB_PER_CHUNK);
+        for (int kb = w.c0 * KB_PER_CHUNK; kb < kb_hi; kb++) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa_hi = base + stage * STAGE_BYTES2;
           const uint32_t sa_lo = sa_hi + A_TILE2;
@@ -479,8 +519,10 @@ sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
       // ===================== MMA issuer (leader CTA) =====================
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
-        for (int kb0 = 0; kb0 < num_kb; kb0 += KB_PER_CHUNK) {
+      Item w;
+      while (next_item(w)) {
+        for (int ch = w.c0; ch < w.c1; ch++) {
+          const int kb0 = ch * KB_PER_CHUNK;
           mbar_wait(tempty_bar(acc), acc_phase ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * PAIR_N;
@@ -517,16 +559,18 @@ sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
     setmaxnreg_inc<224>();
     const int q = warp & 3;           // TMEM lane quarter this warp may access
     const int half = (warp - 4) >> 2; // which 128 of the 256 accumulator columns
+    const int et = threadIdx.x - 128; // 0..255 among the epilogue threads of this CTA
     const uint32_t leader_tempty0 = mapa_shared(tempty_bar(0), 0);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+    Item w;
+    while (next_item(w)) {
       int m0, n0;
-      tile_coords(tile, m0, n0);
+      tile_coords(w.tile, m0, n0);
       float sum[CTA_N];
 #pragma unroll
       for (int j = 0; j < CTA_N; j++) sum[j] = 0.0f;
-      for (int kb0 = 0; kb0 < num_kb; kb0 += KB_PER_CHUNK) {
+      for (int ch = w.c0; ch < w.c1; ch++) {
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + acc * PAIR_N + half * CTA_N + ((uint32_t)(q * 32) << 16);
@@ -542,9 +586,65 @@ sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
         if (lane == 0) mbar_arrive_cluster(leader_tempty0 + 8u * acc);
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
-      const int row = m0 + (int)rank * CTA_M + q * 32 + lane;
-      const int col0 = n0 + half * CTA_N;
-      if (row < m) store_row<CTA_N>(C + row + (long long)col0 * ldc, ldc, sum, n - col0, alpha, beta);
+      const int trow = (int)rank * CTA_M + q * 32 + lane;  // row inside the 256 x 256 tile
+      if (w.c0 == 0 && w.c1 == chunks) {
+        const int row = m0 + trow;
+        const int col0 = n0 + half * CTA_N;
+        if (row < m) store_row<CTA_N>(C + row + (long long)col0 * ldc, ldc, sum, n - col0, alpha, beta);
+        continue;
+      }
+      // ---- stream-K partial: slot layout [column][row] of the whole 256 x 256 tile
+      const int t = w.tile - dp_tiles;
+      const int first = sk_pair_of((long long)t * chunks);
+      const int ncontrib = sk_pair_of((long long)(t + 1) * chunks - 1) - first + 1;
+      float* slots = partial + (size_t)t * sk_slots * (PAIR_M * PAIR_N);
+      {
+        float* mine = slots + (size_t)(pair_id - first) * (PAIR_M * PAIR_N) + (size_t)(half * CTA_N) * PAIR_M + trow;
+#pragma unroll
+        for (int j = 0; j < CTA_N; j++) __stcg(mine + j * PAIR_M, sum[j]);
+      }
+      __threadfence();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (et == 0) {
+        const unsigned int prev = atomicAdd(&counters[t], 1u);
+        const int last = (prev == 2u * (unsigned)ncontrib - 1u);  // both CTAs of every contributing pair
+        if (last) counters[t] = 0;  // self-reset for the next launch
+        s_is_last = last;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const bool last = s_is_last != 0;
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // flag read by all before it can be rewritten
+      if (!last) continue;
+      __threadfence();
+      // this CTA finishes the WHOLE tile (both halves): thread = 4 consecutive rows x 64 columns,
+      // two passes of 32 columns, 32 independent 16-byte loads in flight per contributor
+      const int rg = et & 63, cg = et >> 6;
+      const int row0 = m0 + rg * 4;
+#pragma unroll 1
+      for (int pass = 0; pass < 2; pass++) {
+        const int cbase = cg * 64 + pass * 32;
+        float4 tot[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) tot[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int z = 0; z < ncontrib; z++) {
+          const float* src = slots + (size_t)z * (PAIR_M * PAIR_N) + (size_t)cbase * PAIR_M + rg * 4;
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(src + j * PAIR_M));
+            tot[j].x += v.x; tot[j].y += v.y; tot[j].z += v.z; tot[j].w += v.w;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          const int col = n0 + cbase + j;
+          if (col >= n) continue;
+          float* cp = C + row0 + (long long)col * ldc;
+          const float r[4] = {tot[j].x, tot[j].y, tot[j].z, tot[j].w};
+#pragma unroll
+          for (int e = 0; e < 4; e++)
+            if (row0 + e < m) cp[e] = (beta == 0.0f) ? alpha * r[e] : alpha * r[e] + beta * cp[e];
+        }
+      }
     }
   }
 
@@ -617,7 +717,11 @@ int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const flo
   kb_per_split = (kb_per_split + KB_PER_CHUNK - 1) / KB_PER_CHUNK * KB_PER_CHUNK;
   splits = (total_kb + kb_per_split - 1) / kb_per_split;
   const size_t part_bytes = splits > 1 ? (size_t)splits * tiles1 * BM * BN * sizeof(float) : 0;
-  if (ensure_workspace(ctx, need + part_bytes)) return 1;
+  // + room for the pair kernel's stream-K slots: < 74 leftover tiles x (contributors <= chunks + 2) x 256 KB,
+  // bounded at 512 MB (the plan falls back to whole tiles if it does not fit)
+  const size_t sk_room = std::min<size_t>((size_t)512 << 20,
+                                          (size_t)(tiles2 % 74) * (size_t)((total_kb + 3) / 4 + 2) * 256 * 1024);
+  if (ensure_workspace(ctx, need + std::max(part_bytes, sk_room))) return 1;
   char* ws = (char*)ctx->workspace;
   float *a_hi = (float*)ws, *a_lo = (float*)(ws + offAlo), *b_hi = (float*)(ws + offBhi),
         *b_lo = (float*)(ws + offBlo);
@@ -666,7 +770,30 @@ int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const flo
     g_pair_attr_done = true;
   }
   const int pairs = g_pair_max_clusters;
-  const double cost2 = (double)waves(tiles2, pairs) * (total_kb * 1536.0 + 2500.0);
+  // stream-K over the partial last wave of pair tiles (see the kernel).  Unit = one accumulation
+  // chunk (K = 128, ~3.2 us of a pair); every pair must get at least one unit (contributor ranges
+  // assume no empty segment) and the shortened last wave must save clearly more than the
+  // partial-tile fix-up costs (>= 35 us and >= 3 % of the run; measured: 2304^3 159 -> 143 us,
+  // 2560^3 176 -> 158, 4096^3 548 -> 521, while a predicted saving of 26 us at 2816^3 was a 3 us loss).
+  int sk_tiles = 0, sk_slots = 0;
+  float* sk_partial = nullptr;
+  const int chunks = (total_kb + KB_PER_CHUNK - 1) / KB_PER_CHUNK;
+  if (ctx->opt_sgemm_streamk && tiles2 > 0) {
+    const int rem = (int)(tiles2 % pairs);
+    const long long units = (long long)rem * chunks;
+    const long long seg = units / pairs;
+    const double saved_us = (double)(chunks - (units + pairs - 1) / pairs) * 3.2;
+    const double total_us = (double)waves(tiles2, pairs) * chunks * 3.2;
+    const size_t bytes = (size_t)rem * (size_t)(seg > 0 ? chunks / seg + 2 : 0) * pair::PAIR_M * pair::PAIR_N * sizeof(float);
+    if (rem > 0 && seg >= 1 && saved_us >= 35.0 && saved_us >= 0.03 * total_us && rem <= ctx->num_counters &&
+        need + bytes <= ctx->workspace_bytes) {
+      sk_tiles = rem;
+      sk_slots = (int)(chunks / seg) + 2;
+      sk_partial = (float*)(ws + need);
+    }
+  }
+  const double cost2 = sk_tiles ? ((double)tiles2 * total_kb / pairs) * 1536.0 + 2 * 2500.0 + 15000.0
+                                : (double)waves(tiles2, pairs) * (total_kb * 1536.0 + 2500.0);
   bool use_pair = m >= pair::PAIR_M && n >= pair::PAIR_N && cost2 <= cost1;
   if (ctx->opt_sgemm_pair == 1) use_pair = true;
   if (ctx->opt_sgemm_pair == 2) use_pair = false;
@@ -674,11 +801,12 @@ int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const flo
   if (use_pair) {
     static const char* rg_env = getenv("B200_SGEMM_RASTER");  // tuning: m-tiles per raster group
     const int raster_group = rg_env ? std::max(1, atoi(rg_env)) : 8;
-    const int grid = 2 * (int)std::min<long long>(tiles2, pairs);
+    const int grid = 2 * (int)(sk_tiles ? pairs : std::min<long long>(tiles2, pairs));
     pair::sgemm_3xtf32_pair_kernel<<<grid, pair::THREADS, pair::SMEM_BYTES2, ctx->compute>>>(
-        ma_hi, ma_lo, mb_hi, mb_lo, m, n, k, alpha, beta, C, (long long)ldc, (int)t2m, (int)t2n, raster_group);
+        ma_hi, ma_lo, mb_hi, mb_lo, m, n, k, alpha, beta, C, (long long)ldc, (int)t2m, (int)t2n, raster_group,
+        sk_tiles, sk_slots, sk_partial, ctx->counters);
     B200_CUDA(cudaGetLastError());
-    note_launch(ctx, "sgemm_3xtf32_tcgen05_pair_256x256x32", 2);
+    note_launch(ctx, sk_tiles ? "sgemm_3xtf32_tcgen05_pair_256x256x32_streamk" : "sgemm_3xtf32_tcgen05_pair_256x256x32", 2);
     return 0;
   }
   bool& g_attr_done = g_attr_done_dev[ctx->device % kMaxDevices];

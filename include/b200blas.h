@@ -63,6 +63,7 @@ int b200_ctx_device(const b200_ctx* ctx, int* device, int* sm_count);
  *   "dgemm_tile" = "auto" | "32" | "64" | "128"
  *   "dgemm_tma"  = "on" | "off"   (large aligned DGEMM: TMA-fed kernel vs cp.async kernel)
  *   "dgemm_streamk" = "on" | "off" (TMA kernel: stream-K over the partial last wave of tiles)
+ *   "sgemm_streamk" = "on" | "off" (CTA-pair SGEMM kernel: stream-K over the partial last wave of tiles)
  *   "sgemm_pair" = "auto" | "on" | "off" (tcgen05 SGEMM: CTA-pair 256x256 tiles vs single-CTA 128x128)
  * Defaults come from the environment at context creation: B200_SGEMM, B200_SGEMM_PAIR,
  * B200_DGEMM_TILE, B200_DGEMM_TMA, B200_DGEMM_STREAMK. */

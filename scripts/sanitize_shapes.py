@@ -23,6 +23,7 @@ for dt, m, n, k, opts in cases:
     B = torch.rand(ldb * n, dtype=tdt, device="cuda")
     C = torch.rand(ldc * n, dtype=tdt, device="cuda")
     C0 = C.clone()
+    torch.cuda.synchronize()
     ctx.gemm(dt, m, n, k, 1.25, A, lda, B, ldb, 0.5, C, ldc)
     ctx.sync()
     ref = 1.25 * (A.view(k, lda)[:, :m].double().T @ B.view(n, ldb)[:, :k].double().T) + 0.5 * C0.view(n, ldc)[:, :m].double().T

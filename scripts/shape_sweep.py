@@ -40,6 +40,7 @@ def fill(n, div, tdt):
 
 
 def time_calls(ctx, calls, iters):
+    torch.cuda.synchronize()  # operands were produced on torch's stream
     for i in range(3):
         calls[i % len(calls)]()
     ctx.sync()

@@ -26,6 +26,7 @@ def test_dgemm_streamk(blob, ctx, oracle, shape):
     C = torch.zeros(ldc * n, dtype=torch.float64, device="cuda")
     C2 = torch.zeros_like(C)
     C3 = torch.zeros_like(C)
+    torch.cuda.synchronize()  # inputs are produced on torch's stream, the library runs on its own
     ctx.gemm("f64", m, n, k, 1.0, A, lda, B, ldb, 0.0, C, ldc)
     ctx.sync()
     kern = ctx.last_kernel()
@@ -68,6 +69,7 @@ def test_dgemm_tma_alpha_beta(blob, ctx, oracle, shape, expect):
     B = _fill(torch, k * n, 22, 3.0)
     C0 = _fill(torch, m * n, 23, 11.0)
     C = C0.clone()
+    torch.cuda.synchronize()
     ctx.gemm("f64", m, n, k, 1.5, A, m, B, k, -0.25, C, m)
     ctx.sync()
     kern = ctx.last_kernel()
