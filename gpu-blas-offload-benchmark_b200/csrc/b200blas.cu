@@ -287,7 +287,7 @@ int b200_alloc(b200_ctx* ctx, int mode, size_t bytes, void** host, void** dev) {
     // managed blocks are pooled too: cudaMallocManaged / cudaFree churn leaves
     // asynchronous UVM driver work (unmap, page-table teardown) that lands in the
     // next timed region
-    if (ensure_workspace(ctx, std::min<size_t>(4 * bytes + ((size_t)32 << 20), (size_t)24 << 30))) return 1;
+    if (ensure_workspace(ctx, std::min<size_t>(4 * bytes + ((size_t)96 << 20), (size_t)24 << 30))) return 1;
     const size_t cap = round_capacity_managed(bytes);
     void* p = cache_take(ctx->managed_cache, cap);
     if (!p) B200_CUDA(cudaMallocManaged(&p, cap, cudaMemAttachGlobal));
@@ -298,8 +298,8 @@ int b200_alloc(b200_ctx* ctx, int mode, size_t bytes, void** host, void** dev) {
   B200_REQUIRE(mode == B200_OFFLOAD_ALWAYS || mode == B200_OFFLOAD_ONCE,
                "b200_alloc: unknown offload mode %d", mode);
   // Grow the scratch workspace here, where the harness is not timing: the 3xTF32
-  // operand splits need 2 x (|A| + |B|), split-K partials far less.
-  if (ensure_workspace(ctx, std::min<size_t>(4 * bytes + ((size_t)32 << 20), (size_t)24 << 30))) return 1;
+  // operand splits need 2 x (|A| + |B|), split-K / stream-K partial tiles at most ~56 MB.
+  if (ensure_workspace(ctx, std::min<size_t>(4 * bytes + ((size_t)96 << 20), (size_t)24 << 30))) return 1;
   const size_t cap = round_capacity(bytes);
   void* alias = nullptr;
   void* h = cache_take(ctx->pinned_cache, cap, &alias);

@@ -717,10 +717,11 @@ int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const flo
   kb_per_split = (kb_per_split + KB_PER_CHUNK - 1) / KB_PER_CHUNK * KB_PER_CHUNK;
   splits = (total_kb + kb_per_split - 1) / kb_per_split;
   const size_t part_bytes = splits > 1 ? (size_t)splits * tiles1 * BM * BN * sizeof(float) : 0;
-  // + room for the pair kernel's stream-K slots: < 74 leftover tiles x (contributors <= chunks + 2) x 256 KB,
-  // bounded at 512 MB (the plan falls back to whole tiles if it does not fit)
-  const size_t sk_room = std::min<size_t>((size_t)512 << 20,
-                                          (size_t)(tiles2 % 74) * (size_t)((total_kb + 3) / 4 + 2) * 256 * 1024);
+  // + room for the pair kernel's stream-K slots: rem tiles x (pairs / rem + 2) contributors x 256 KB
+  // = (pairs + 2 rem) x 256 KB <= 56 MB whatever the problem size; b200_alloc pre-sizes the workspace
+  // for it so that this call does not reallocate inside a timed region
+  const int pairs_est = std::max(1, P / 2);
+  const size_t sk_room = (size_t)(pairs_est + 2 * (int)(tiles2 % pairs_est)) * pair::PAIR_M * pair::PAIR_N * sizeof(float);
   if (ensure_workspace(ctx, need + std::max(part_bytes, sk_room))) return 1;
   char* ws = (char*)ctx->workspace;
   float *a_hi = (float*)ws, *a_lo = (float*)(ws + offAlo), *b_hi = (float*)(ws + offBhi),
