@@ -12,7 +12,10 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("dt,shape", [("f64", (2048, 2048, 2048)), ("f64", (1536, 2300, 4100)), ("f64", (4096, 4096, 3000)),
-                                      ("f32", (2048, 2048, 2048)), ("f32", (3000, 2500, 1100)), ("f64", (1030, 4100, 1026))],
+                                      ("f32", (2048, 2048, 2048)), ("f32", (3000, 2500, 1100)), ("f64", (1030, 4100, 1026)),
+                                      # compute-bound regime (FP64 from ~5500^3): interleaved A / B uploads, 6 x 6 pieces,
+                                      # K-chunk runs joined into one GEMM -- the path bench.py's e2e number takes
+                                      ("f64", (6144, 6144, 6144)), ("f64", (5900, 6100, 5700))],
                          ids=lambda v: v if isinstance(v, str) else "x".join(map(str, v)))
 def test_gemm_block_pipeline(blob, ctx, oracle, dt, shape):
     m, n, k = shape
