@@ -2,31 +2,41 @@
 """bench.py -- headline benchmark of the B200 backend for GPU-BLOB.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
-                    [--workload dgemm|sgemm|dgemv|sgemv] [--dim D] [--no-extras]
+                    [--workload dgemm|sgemm|dgemv|sgemv] [--dim D] [--no-extras] [--weak]
 
 One "step" is one pass of the hot path over one batch of synthetic input: one
 GEMM (or GEMV) call of the named workload.  Metric = GFLOP/s with the
 reference's own FLOP formulas (include/doGemm.hh:493-505 -> 2MNK + MN;
 include/doGemv.hh:377-388 -> 2MN + M), as BASELINE.json asks.
 
-N = 1 default workload: square DGEMM M=N=K=8192, the top of BASELINE.json
-configs[1] ("square DGEMM/SGEMM M=N=K 1->8192 on 1 B200").
-N > 1 (torchrun, one rank per GPU): the same per-GPU problem as a column slab of
-a wider one -- M=K=8192, N = 8192 x world_size; A replicated by an NCCL
-broadcast over NVLink, B and C column slabs stay local (no data-path
-collective inside a step), scaling = "weak".
+N = 1   square DGEMM M=N=K=8192, the top of BASELINE.json configs[1]
+        ("square DGEMM/SGEMM M=N=K 1->8192 on 1 B200").
+N > 1   (torchrun, one rank per GPU) BASELINE.json configs[4]: ONE square problem
+        M=N=K=32768 partitioned over the N GPUs ("scaling": "strong") through the library's
+        multi-GPU team (csrc/mg.cu, one rank per process, peers mapped by CUDA IPC): rank r
+        owns a column slab of B and C and a K-share of A; every step the shares are pushed to
+        all replicas of A over NVLink chunk by chunk while the GEMM consumes them, and the
+        C slabs are gathered on rank 0 -- the exchange is INSIDE the timed step.
+        --weak restores round 1's independent 8192-wide slabs (no exchange in the step).
 
-value      device-resident: operands already in HBM, CUDA events on the
-           library's compute stream around exactly K steps.
-e2e        the same call through the reference-facing plugin path with HOST
-           buffers: b200_?gemm_offload / b200_?gemv_offload (what
-           gpu::gemm_gpu<T>::callGemm does in Always mode): pinned H2D of A and
-           B, kernel, D2H of C every step.
-roofline   achieved FLOP/s (or GB/s) of the dominant kernel vs the measured
-           peak of the pipe that bounds it.
+value      device-resident: operands already in HBM (N > 1: each rank's K-share of A and its
+           slab of B), CUDA events on the library's compute stream around exactly K steps,
+           max over ranks.
+e2e        the same step through the reference-facing plugin path with HOST buffers, copies
+           inside the timed region: N = 1 b200_?gemm_offload (gpu::gemm_gpu<T>::callGemm in
+           Always mode); N > 1 the team's upload + replicate + compute + download step (what
+           the backend classes run with B200_NGPUS=N), every rank uploading only its share of
+           A and its slab of B over its own PCIe link and downloading its slab of C.
+roofline   achieved FLOP/s (or GB/s) of the dominant kernel vs the measured peak of the pipe
+           that bounds it (+ the spec-derived figure).
 cpu_baseline / --impl reference
-           the reference's own CPU path (cblas_dgemm from its OpenBLAS backend,
-           oracle/_ref/libblobref.so) on this box's host cores.
+           the reference's own CPU path -- cpu::gemm_cpu<T>::compute() of its OpenBLAS backend
+           (include/kernels/gemm.hh:19-42, OpenBLAS/gemm.hh:25-43), compiled from
+           /root/reference into oracle/_ref/libblobref.so -- on this box's host cores, at the
+           size stated in config.workload.
+gpu_baseline
+           the reference's cuBLAS backend classes (cuBLAS/gemm.hh) through
+           oracle/_ref/blobref-cublas, run as a separate process outside every timed region.
 """
 import argparse
 import ctypes
@@ -38,11 +48,16 @@ import sys
 import threading
 import time
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # the team's streams never share a hardware queue
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 ELEM = {"f64": 8, "f32": 4}
+TOL = {"f64": 1e-12, "f32": 1e-5}
+STRONG_DIM = 32768          # BASELINE.json configs[4]
+CPU_REF_GEMM_DIM = 8192     # largest GEMM the reference arm runs whole (32768^3 is ~47 s per step on 16 cores)
 
 
 def gemm_flops(m, n, k):  # include/doGemm.hh:493-505, BETA == 0
@@ -63,16 +78,17 @@ def gemv_bytes(m, n, s):  # include/doGemv.hh:391-395
 
 def ncu_traffic(workload, kernel_name):
     """DRAM bytes (read + write) of ONE launch of the dominant kernel, from the committed
-    `ncu --set full` capture of this workload's bench command (profiles/r1_traffic.json,
-    written by scripts/ncu_traffic.py from the .ncu-rep); None when the capture is of a
-    different kernel than the one that just ran."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if not os.path.exists(p):
-        return None, None
-    t = json.load(open(p)).get(workload)
-    if not t or t.get("kernel_label") != kernel_name:
-        return None, None
-    return t["dram_read_bytes"] + t["dram_write_bytes"], t.get("source")
+    `ncu --set full` capture of this workload's bench command (profiles/r2_traffic.json, else
+    r1_traffic.json; written by scripts/ncu_traffic.py from the .ncu-rep); None when the capture
+    is of a different kernel than the one that just ran."""
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if not os.path.exists(p):
+            continue
+        t = json.load(open(p)).get(workload)
+        if t and t.get("kernel_label") == kernel_name:
+            return t["dram_read_bytes"] + t["dram_write_bytes"], t.get("source")
+    return None, None
 
 
 def measured_peaks():
@@ -134,6 +150,10 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def prefix(dtype):
+    return "d" if dtype == "f64" else "s"
+
+
 # ---------------------------------------------------------------- reference arm
 
 def load_reference():
@@ -143,104 +163,133 @@ def load_reference():
                         stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     lib = ctypes.CDLL(so)
     lib.blobref_blas_config.restype = ctypes.c_char_p
-    d, f, i, vp = ctypes.c_double, ctypes.c_float, ctypes.c_int, ctypes.c_void_p
-    lib.blobref_cblas_dgemm.argtypes = [i, i, i, i, i, d, vp, i, vp, i, d, vp, i]
-    lib.blobref_cblas_sgemm.argtypes = [i, i, i, i, i, f, vp, i, vp, i, f, vp, i]
-    lib.blobref_cblas_dgemv.argtypes = [i, i, i, d, vp, i, vp, i, d, vp, i]
-    lib.blobref_cblas_sgemv.argtypes = [i, i, i, f, vp, i, vp, i, f, vp, i]
+    i, vp = ctypes.c_int, ctypes.c_void_p
+    pd = ctypes.POINTER(ctypes.c_double)
+    for name in ("blobref_dgemm", "blobref_sgemm"):
+        getattr(lib, name).argtypes = [i, i, i, i, vp, pd, pd]
+    for name in ("blobref_dgemv", "blobref_sgemv"):
+        getattr(lib, name).argtypes = [i, i, i, vp, pd, pd]
     return lib
 
 
-def reference_step_fn(lib, kind, dtype, dim):
-    """One step of the reference CPU path: the cblas call its OpenBLAS backend
-    issues (OpenBLAS/gemm.hh:27-33, OpenBLAS/gemv.hh:27-31) on resident inputs
-    drawn from the reference's value distribution."""
-    import numpy as np
-    t = np.float64 if dtype == "f64" else np.float32
-    rng = np.random.default_rng(19123005)
-    if kind == "gemm":
-        A = (rng.integers(0, 100, dim * dim) / 7.0).astype(t)
-        B = (rng.integers(0, 100, dim * dim) / 3.0).astype(t)
-        C = np.zeros(dim * dim, t)
-        fn = lib.blobref_cblas_dgemm if dtype == "f64" else lib.blobref_cblas_sgemm
-        return (lambda: fn(0, 0, dim, dim, dim, 1.0, A.ctypes.data, dim, B.ctypes.data, dim, 0.0,
-                           C.ctypes.data, dim)), gemm_flops(dim, dim, dim), (A, B, C)
-    A = (rng.integers(0, 100, dim * dim) / 7.0).astype(t)
-    x = (rng.integers(0, 100, dim) / 3.0).astype(t)
-    y = np.zeros(dim, t)
-    fn = lib.blobref_cblas_dgemv if dtype == "f64" else lib.blobref_cblas_sgemv
-    return (lambda: fn(0, dim, dim, 1.0, A.ctypes.data, dim, x.ctypes.data, 1, 0.0, y.ctypes.data, 1)), \
-        gemv_flops(dim, dim), (A, x, y)
-
-
-def cpu_sample_dim(kind, dim):
-    # bounded sample: OpenBLAS GFLOP/s is flat above 4096 (BASELINE.md section 2)
-    return min(dim, 4096) if kind == "gemm" else min(dim, 16384)
+def reference_dims(kind, dim):
+    """The size the CPU arm runs WHOLE.  GEMM is capped at 8192^3 (config 5's 32768^3 is ~47 s
+    per step on the box's cores); the cap is stated in config.workload, never hidden."""
+    return min(dim, CPU_REF_GEMM_DIM) if kind == "gemm" else dim
 
 
 def time_reference(kind, dtype, dim, steps, warmup):
+    """`steps` iterations of the reference's own cpu::gem?_cpu<T>::compute() -- its generator
+    (srand(19123005), rand() % 100 / 7.0 and / 3.0), its cblas call + consume(), its
+    wall-clock timer (include/kernels/gemm.hh:19-42) -- at M=N(=K)=dim."""
     lib = load_reference()
     cores = os.cpu_count() or 1
     lib.blobref_blas_set_threads(min(cores, 64))  # OpenBLAS build: MAX_THREADS=64
-    sdim = cpu_sample_dim(kind, dim)
-    step, flops, keep = reference_step_fn(lib, kind, dtype, sdim)
-    for _ in range(warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
-    dt = time.perf_counter() - t0
+    cs, sec = ctypes.c_double(), ctypes.c_double()
+
+    def run(iters):
+        if kind == "gemm":
+            fn = lib.blobref_dgemm if dtype == "f64" else lib.blobref_sgemm
+            fn(dim, dim, dim, iters, None, ctypes.byref(cs), ctypes.byref(sec))
+        else:
+            fn = lib.blobref_dgemv if dtype == "f64" else lib.blobref_sgemv
+            fn(dim, dim, iters, None, ctypes.byref(cs), ctypes.byref(sec))
+        return sec.value
+
+    if warmup > 0:
+        run(warmup)
+    dt = run(steps)
+    flops = gemm_flops(dim, dim, dim) if kind == "gemm" else gemv_flops(dim, dim)
     return {"value": flops * steps / dt * 1e-9, "ms_per_step": dt / steps * 1e3,
-            "cores": lib.blobref_blas_threads(), "kind": "reference",
-            "sample": f"{'d' if dtype == 'f64' else 's'}{kind} M=N{'=K' if kind == 'gemm' else ''}={sdim}, "
-                      f"{steps} calls of the reference's cblas_* (OpenBLAS) path; "
-                      f"{lib.blobref_blas_config().decode().strip()}"}
+            "cores": lib.blobref_blas_threads(), "kind": "reference", "checksum": cs.value,
+            "sample": f"{prefix(dtype)}{kind} M=N{'=K' if kind == 'gemm' else ''}={dim}: {steps} iterations inside one "
+                      f"cpu::gem{'m' if kind == 'gemm' else 'v'}_cpu<T>::compute() of the reference (its generator, "
+                      f"cblas call + consume(), its timer); {lib.blobref_blas_config().decode().strip()}"}
 
 
-def run_reference_arm(args, kind, dtype, dim):
+def run_reference_arm(args, kind, dtype, dim, strong):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = time_reference(kind, dtype, dim, args.steps, args.warmup)
+    rdim = reference_dims(kind, dim)
+    r = time_reference(kind, dtype, rdim, args.steps, args.warmup)
+    cfg = workload_config(kind, dtype, dim, args.gpus, strong)
+    if rdim != dim:
+        cfg["workload"] = (f"{prefix(dtype)}gemm_square M=N=K={rdim} -- BOUNDED SAMPLE of the {args.gpus}-GPU workload "
+                           f"M=N=K={dim} (one {dim}^3 step is ~{gemm_flops(dim, dim, dim) / (r['value'] * 1e9):.0f} s "
+                           "on these host cores); the rate, not the size, is what carries over")
+        cfg["sampled"] = True
+    elif args.gpus > 1:
+        cfg["workload"] = f"{prefix(dtype)}{kind}_square M=N{'=K' if kind == 'gemm' else ''}={rdim} (the whole problem the {args.gpus} GPUs partition)"
     line = {
         "impl": "reference",
-        "metric": f"{'D' if dtype == 'f64' else 'S'}{kind.upper()} GFLOP/s (GPU-BLOB formula)",
+        "metric": f"{prefix(dtype).upper()}{kind.upper()} GFLOP/s (GPU-BLOB formula)",
         "value": r["value"], "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-        "scaling": "strong" if (args.strong and args.gpus > 1) else "weak", "vs_baseline": None,
-        "dtype": dtype, "data": "synthetic",
-        "config": workload_config(kind, dtype, dim, args.gpus, args.strong),
+        "scaling": "strong" if (strong and args.gpus > 1) else "weak", "vs_baseline": None,
+        "dtype": dtype, "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": r["value"], "unit": "GFLOP/s", "cores": r["cores"],
                          "kind": r["kind"], "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "checksum": r["checksum"],
     }
     print(json.dumps(line), flush=True)
 
 
+def cublas_baseline(kind, dtype, dim):
+    """The reference's cuBLAS backend (its own classes, its own timer) in a separate process:
+    Once mode = kernel rate with resident operands, Always mode = its end-to-end rate."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "blobref-cublas")
+    if not os.path.exists(exe):
+        return {"unavailable": "oracle/_ref/blobref-cublas not built"}
+    out = {"impl": "reference cuBLAS backend (cuBLAS/gemm.hh, cuBLAS/gemv.hh) via oracle/_ref/blobref-cublas",
+           "unit": "GFLOP/s", "size": dim,
+           "note": "its SGEMM runs under CUBLAS_TENSOR_OP_MATH (cuBLAS/gemm.hh:53)"}
+    dims = [str(dim)] * (3 if kind == "gemm" else 2)
+    for mode, iters in (("once", 10), ("always", 5)):
+        try:
+            r = subprocess.run([exe, prefix(dtype) + kind, mode] + dims + [str(iters), "2"], capture_output=True,
+                               text=True, timeout=300, cwd=os.path.dirname(exe))
+            rows = [ln.split() for ln in r.stdout.strip().splitlines() if len(ln.split()) == 3]
+            if r.returncode != 0 or not rows:
+                out[mode] = {"error": (r.stdout + r.stderr)[-200:]}
+                continue
+            # second repeat: the handle, the streams and the allocator are warm (the harness keeps one object too)
+            out[mode] = {"gflops": float(rows[-1][2]), "seconds": float(rows[-1][1]), "iterations": iters,
+                         "checksum": float(rows[-1][0])}
+        except (OSError, subprocess.TimeoutExpired) as ex:
+            out[mode] = {"error": str(ex)[-200:]}
+    return out
+
+
 # ------------------------------------------------------------------- own arm
 
-def workload_config(kind, dtype, dim, gpus, strong=False):
-    p = "d" if dtype == "f64" else "s"
+def workload_config(kind, dtype, dim, gpus, strong=True):
+    p = prefix(dtype)
     if gpus > 1 and strong:
-        wl = (f"{p}gemm M=N=K={dim} in {gpus} column slabs ({dim // gpus} columns of B and C per GPU, A replicated)"
+        wl = (f"{p}gemm M=N=K={dim} in {gpus} column slabs (~{dim // gpus} columns of B and C and a K-share of "
+              f"~{dim // gpus} columns of A per GPU; A replicated over NVLink and C gathered inside every step)"
               if kind == "gemm" else
-              f"{p}gemv M=N={dim} in {gpus} row blocks ({dim // gpus} rows of A and y per GPU, x replicated)")
+              f"{p}gemv M=N={dim} in {gpus} row blocks (~{dim // gpus} rows of A and y per GPU; x replicated over "
+              "NVLink and y gathered inside every step)")
+        base = "configs[4]"
     elif kind == "gemm":
         wl = f"{p}gemm_square M=N=K={dim}" if gpus == 1 else \
             f"{p}gemm column slabs: M=K={dim}, N={dim}x{gpus} ({dim} columns of B and C per GPU, A replicated)"
+        base = "configs[1]"
     else:
         wl = f"{p}gemv_square M=N={dim}" if gpus == 1 else \
             f"{p}gemv row blocks: N={dim}, M={dim}x{gpus} ({dim} rows of A and y per GPU, x replicated)"
-    return {"workload": wl, "baseline_config": "configs[1]" if kind == "gemm" else "configs[3]",
+        base = "configs[3]"
+    return {"workload": wl, "baseline_config": base,
             "alpha": 1, "beta": 0, "layout": "column-major, NoTrans",
             "l2": "operands larger than the 126 MB L2 (no flush needed)",
             "inputs": "rand()%100 / 7.0 and / 3.0 value distribution of the reference generator"}
 
 
 def device_inputs(torch, kind, dtype, dim, seed, loc=None):
-    """loc = this rank's extent of the partitioned dimension (columns of B/C for GEMM,
-    rows of A/y for GEMV); dim when there is one rank or the scaling is weak."""
+    """loc = this rank's extent of the partitioned dimension (weak scaling / one GPU: dim)."""
     loc = loc or dim
     tdt = torch.float64 if dtype == "f64" else torch.float32
     g = torch.Generator(device="cuda").manual_seed(seed)
@@ -250,6 +299,17 @@ def device_inputs(torch, kind, dtype, dim, seed, loc=None):
     if kind == "gemm":
         return fill(dim * dim, 7.0), fill(dim * loc, 3.0), torch.zeros(dim * loc, dtype=tdt, device="cuda")
     return fill(loc * dim, 7.0), fill(dim, 3.0), torch.zeros(loc, dtype=tdt, device="cuda")
+
+
+def host_fill(view, div, seed):
+    """Reference value distribution into a (large) pinned buffer: one random block of a prime
+    length, repeated -- fast, and a misplaced chunk would not line up with the repetition."""
+    import numpy as np
+    period = min(view.size, (1 << 23) + 11)
+    block = (np.random.default_rng(seed).integers(0, 100, period) / div).astype(view.dtype)
+    for o in range(0, view.size, period):
+        n = min(period, view.size - o)
+        view[o:o + n] = block[:n]
 
 
 def time_device(ctx, call, steps, warmup, barrier):
@@ -268,10 +328,12 @@ def time_device(ctx, call, steps, warmup, barrier):
 
 
 def bench_kernel(blob, ctx, torch, kind, dtype, dim, steps, warmup, barrier=lambda: None, seed=1):
-    """Device-resident timing of one workload; returns dict."""
+    """Device-resident timing of one workload on one GPU; returns dict."""
     a, b, c = device_inputs(torch, kind, dtype, dim, seed)
     torch.cuda.synchronize()
     if kind == "gemm":
+        if dtype == "f32":
+            ctx.sgemm_prepare(dim, dim, dim, dim, dim)
         call = lambda: ctx.gemm(dtype, dim, dim, dim, 1.0, a, dim, b, dim, 0.0, c, dim)
         flops, nbytes = gemm_flops(dim, dim, dim), gemm_bytes(dim, dim, dim, ELEM[dtype])
     else:
@@ -287,23 +349,18 @@ def bench_kernel(blob, ctx, torch, kind, dtype, dim, steps, warmup, barrier=lamb
 
 def bench_e2e(blob, ctx, kind, dtype, dim, steps, warmup, barrier=lambda: None):
     """Host buffers -> C-ABI offload call -> host result, copies inside the timed region."""
-    import numpy as np
     s = ELEM[dtype]
     md = blob.OFFLOAD_ALWAYS
-    if kind == "gemm":
-        counts = (dim * dim, dim * dim, dim * dim)
-    else:
-        counts = (dim * dim, dim, dim)
+    counts = (dim * dim, dim * dim, dim * dim) if kind == "gemm" else (dim * dim, dim, dim)
     ops = [ctx.alloc(md, cnt * s) for cnt in counts]
     views = [blob.host_view(h, cnt, dtype) for (h, _), cnt in zip(ops, counts)]
-    rng = np.random.default_rng(5)
-    chunk = 1 << 24
-    for v, div in zip(views[:2], (7.0, 3.0)):
-        for o in range(0, v.size, chunk):
-            v[o:o + chunk] = rng.integers(0, 100, min(chunk, v.size - o)) / div
+    host_fill(views[0], 7.0, 5)
+    host_fill(views[1], 3.0, 6)
     views[2][:] = 0
     (hA, dA), (hB, dB), (hC, dC) = ops
     if kind == "gemm":
+        if dtype == "f32":
+            ctx.sgemm_prepare(dim, dim, dim, dim, dim)
         call = lambda: ctx.gemm_offload(dtype, dim, dim, dim, 1.0, hA, dA, dim, hB, dB, dim, 0.0, hC, dC, dim)
         flops = gemm_flops(dim, dim, dim)
         h2d, d2h = 2 * dim * dim * s, dim * dim * s
@@ -328,63 +385,323 @@ def bench_e2e(blob, ctx, kind, dtype, dim, steps, warmup, barrier=lambda: None):
             "launches": launches, "checksum": checksum}
 
 
-def bench_e2e_multi(blob, ctx, torch, dist, kind, dtype, dim, steps, warmup, barrier, rank, world, loc):
-    """N > 1 end to end.  Every step: each rank uploads its 1/N share of the replicated
-    operand (A for GEMM, x for GEMV) over its OWN PCIe link, an NCCL all-gather over
-    NVLink replicates it on every GPU, and each rank uploads its slab (B columns / A
-    rows), runs the kernel and downloads its slab of the result (C columns / y rows) to
-    its own pinned host buffer."""
+def kernel_roofline(ctx, peaks, peak_src, kind, dtype, gflops, gbs, kernel_name, flops, nbytes):
+    """roofline object of one kernel: measured peak of the pipe that bounds it + the spec figure."""
+    if kind == "gemm" and dtype == "f64":
+        pk, pk2 = ctx.probe_peak("dmma"), ctx.probe_peak("dfma")  # GFLOP/s, measured live on this GPU
+        peak = max(pk, pk2)
+        r = {"bound": "tensor", "achieved": gflops / 1e3, "peak": peak / 1e3, "unit": "TFLOP/s",
+             "frac": gflops / peak, "traffic": None, "kernel": kernel_name,
+             "peak_source": "FP64 tensor (DMMA) pipe: b200_probe_peak(dmma) measured live on this GPU; "
+                            "MEASURED_PEAKS.json holds no FP64 peak",
+             "peak_spec": 37.2, "frac_of_spec": gflops / 37.2e3,
+             "peak_spec_source": "148 SMs x 64 FP64 FMA/clk x 2 x 1.965 GHz (SURVEY.md section 6)",
+             "probe_dfma_tflops": pk2 / 1e3, "probe_dmma_tflops": pk / 1e3}
+    elif kind == "gemm":
+        # 3xTF32: three tensor-core MMAs per FP32 product.  TF32 runs at half the bf16 rate, so the
+        # measured denominator is MEASURED_PEAKS bf16_tflops / 2 / 3.
+        ffma = ctx.probe_peak("ffma")
+        tc_kernel = "tcgen05" in kernel_name
+        peak = peaks["bf16_tflops"] * 1e3 / 2.0 / 3.0 if tc_kernel else ffma
+        r = {"bound": "tensor" if tc_kernel else "fp32-pipe", "achieved": gflops / 1e3,
+             "peak": peak / 1e3, "unit": "TFLOP/s", "frac": gflops / peak, "traffic": None, "kernel": kernel_name,
+             "peak_source": (f"bf16_tflops of {peak_src} / 2 (TF32 = half the bf16 tensor rate) / 3 "
+                             "(3xTF32: three MMAs per FP32 product)") if tc_kernel else
+                            "b200_probe_peak(ffma) measured live on this GPU",
+             "peak_spec": 375.0 if tc_kernel else 74.5, "frac_of_spec": gflops / (375e3 if tc_kernel else 74.5e3),
+             "peak_spec_source": "2250 TFLOP/s dense bf16 / 2 / 3" if tc_kernel else "148 SMs x 128 FFMA/clk x 2 x 1.965 GHz",
+             "probe_ffma_tflops": ffma / 1e3, "frac_of_ffma_peak": gflops / ffma}
+    else:
+        r = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+             "frac": gbs / peaks["hbm_gbs"], "traffic": None, "kernel": kernel_name,
+             "peak_source": f"hbm_gbs of {peak_src} (burst copy figure; a GEMV only reads)",
+             "peak_spec": 7700.0, "frac_of_spec": gbs / 7700.0, "peak_spec_source": "HBM3e nominal 7.7 TB/s"}
+    r["algorithmic_bytes"] = nbytes
+    r["algorithmic_flops"] = flops
+    return r
+
+
+def e2e_path(kind, dtype, world):
+    p, mv = prefix(dtype), ("m" if kind == "gemm" else "v")
+    if world == 1:
+        return f"b200_{p}gem{mv}_offload (Always mode of gpu::gem{mv}_gpu<T>), pinned host buffers"
+    return (f"b200_mg_gem{mv} with B200_MG_UPLOAD|REPLICATE|COMPUTE|DOWNLOAD (the Always-mode step of gpu::gem{mv}_gpu<T> "
+            "under B200_NGPUS, one rank per process): per rank and step, H2D of its share of "
+            + ("A and its slab of B" if kind == "gemm" else "x and its row block of A") +
+            " from pinned host buffers, shares pushed to every peer over NVLink while the kernels run, "
+            "D2H of its slab of the result; b200_mg_sync")
+
+
+def run_single(args, kind, dtype, dim, torch, blob, local):
+    ctx = blob.Context(local)
+    barrier = torch.cuda.synchronize
+    a, b, c = device_inputs(torch, kind, dtype, dim, seed=1)
+    torch.cuda.synchronize()
+    if kind == "gemm":
+        if dtype == "f32":
+            ctx.sgemm_prepare(dim, dim, dim, dim, dim)
+        call = lambda: ctx.gemm(dtype, dim, dim, dim, 1.0, a, dim, b, dim, 0.0, c, dim)
+        flops, nbytes = gemm_flops(dim, dim, dim), gemm_bytes(dim, dim, dim, ELEM[dtype])
+    else:
+        call = lambda: ctx.gemv(dtype, dim, dim, 1.0, a, dim, b, 1, 0.0, c, 1)
+        flops, nbytes = gemv_flops(dim, dim), gemv_bytes(dim, dim, ELEM[dtype])
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms, launches = time_device(ctx, call, args.steps, args.warmup, barrier)
+    clocks = sampler.stop()
+    kernel_name = ctx.last_kernel()
+    value = flops * args.steps / (ms * 1e-3) * 1e-9
+    gbs = nbytes * args.steps / (ms * 1e-3) * 1e-9
+    del a, b, c
+    torch.cuda.empty_cache()
+
+    e2e_steps = max(1, min(args.steps, 5))
+    e = bench_e2e(blob, ctx, kind, dtype, dim, e2e_steps, 1, barrier)
+
+    peaks, peak_src = measured_peaks()
+    roofline = kernel_roofline(ctx, peaks, peak_src, kind, dtype, value, gbs, kernel_name, flops, nbytes)
+    traffic, traffic_src = ncu_traffic(args.workload, kernel_name) if dim == default_dim(kind) else (None, None)
+    roofline["traffic"], roofline["traffic_source"] = traffic, traffic_src
+
+    # --- the other three kernels at their headline sizes: value, roofline and e2e each --------
+    extras = {}
+    if not args.no_extras:
+        for (k2, d2, n2) in (("gemm", "f64", 8192), ("gemm", "f32", 8192), ("gemv", "f64", 32768), ("gemv", "f32", 32768)):
+            if (k2, d2, n2) == (kind, dtype, dim):
+                continue
+            key = f"{prefix(d2)}{k2}_{n2}"
+            try:
+                r = bench_kernel(blob, ctx, torch, k2, d2, n2, max(3, min(args.steps, 10)), 3)
+                torch.cuda.empty_cache()
+                e2 = bench_e2e(blob, ctx, k2, d2, n2, 3, 1)
+                rf = kernel_roofline(ctx, peaks, peak_src, k2, d2, r["gflops"], r["gbs"], r["kernel"], r["flops"], r["bytes"])
+                rf["traffic"], rf["traffic_source"] = ncu_traffic(prefix(d2) + k2, r["kernel"])
+                extras[key] = {"gflops": round(r["gflops"], 1), "ms": round(r["ms_per_step"], 4), "kernel": r["kernel"],
+                               "launches_per_step": r["launches"] / max(3, min(args.steps, 10)),
+                               "roofline": rf,
+                               "e2e": {"value": round(e2["gflops"], 1), "unit": "GFLOP/s", "h2d_bytes_per_step": e2["h2d"],
+                                       "d2h_bytes_per_step": e2["d2h"], "path": e2e_path(k2, d2, 1)}}
+            except Exception as ex:  # noqa: BLE001 -- explanatory only
+                extras[key] = {"error": str(ex)[-300:]}
+            torch.cuda.empty_cache()
+        try:
+            extras["probe_ffma_tflops"] = round(ctx.probe_peak("ffma") / 1e3, 2)
+            extras["probe_copy_gbs"] = round(ctx.probe_peak("copy"), 1)
+        except Exception as ex:  # noqa: BLE001
+            extras["probe_error"] = str(ex)
+    ctx.close()
+    torch.cuda.empty_cache()
+
+    # --- reported baselines, both outside every timed region ---------------------------------
+    cpu = time_reference(kind, dtype, reference_dims(kind, dim), 5 if kind == "gemm" else 10, 0)
+    gpu_base = cublas_baseline(kind, dtype, dim)
+
+    line = {
+        "metric": f"{prefix(dtype).upper()}{kind.upper()} GFLOP/s (GPU-BLOB formula)",
+        "value": value, "unit": "GFLOP/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": dtype, "data": "synthetic", "config": workload_config(kind, dtype, dim, 1),
+        "clocks": clocks,
+        "e2e": {"value": e["gflops"], "unit": "GFLOP/s", "h2d_bytes_per_step": e["h2d"],
+                "d2h_bytes_per_step": e["d2h"], "steps": e2e_steps, "path": e2e_path(kind, dtype, 1)},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "cpu_baseline": {"value": cpu["value"], "unit": "GFLOP/s", "cores": cpu["cores"], "kind": cpu["kind"],
+                         "sample": cpu["sample"]},
+        "gpu_baseline": gpu_base,
+        "kernel": kernel_name,
+        "extras": extras,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_team(args, kind, dtype, dim, torch, dist, blob, rank, world, local):
+    """N > 1, strong scaling: one problem partitioned over the team (rank mode, CUDA IPC)."""
     import numpy as np
     s = ELEM[dtype]
-    tdt = torch.float64 if dtype == "f64" else torch.float32
-    md = blob.OFFLOAD_ONCE
-    rep_count = dim * dim if kind == "gemm" else dim          # A / x
-    share = (rep_count + world - 1) // world                  # this rank's piece of it
-    slab_count = dim * loc                                    # B slab / A row block
-    out_count = dim * loc if kind == "gemm" else loc          # C slab / y block
-    h_share, _d = ctx.alloc(md, share * s)
-    h_slab, d_slab = ctx.alloc(md, slab_count * s)
-    h_out, d_out = ctx.alloc(md, out_count * s)
-    rep_t = torch.zeros(share * world, dtype=tdt, device="cuda")   # NCCL needs torch tensors
-    share_t = torch.zeros(share, dtype=tdt, device="cuda")
-    rng = np.random.default_rng(7 + rank)
-    for h, cnt, div in ((h_slab, slab_count, 3.0 if kind == "gemm" else 7.0),
-                        (h_share, share, 7.0 if kind == "gemm" else 3.0)):
-        v = blob.host_view(h, cnt, dtype)
-        for o in range(0, v.size, 1 << 24):
-            v[o:o + (1 << 24)] = rng.integers(0, 100, min(1 << 24, v.size - o)) / div
+    npdt = np.float64 if dtype == "f64" else np.float32
 
-    def step():
-        ctx.h2d(share_t, h_share, share * s, 0)
-        ctx.h2d(d_slab, h_slab, slab_count * s, 1)
-        ctx.sync()
-        dist.all_gather_into_tensor(rep_t, share_t)
+    def exchange(b):
+        out = [None] * world
+        dist.all_gather_object(out, b)
+        return out
+
+    def barrier():
+        dist.barrier()
         torch.cuda.synchronize()
-        if kind == "gemm":
-            ctx.gemm(dtype, dim, loc, dim, 1.0, rep_t, dim, d_slab, dim, 0.0, d_out, dim)
-        else:
-            ctx.gemv(dtype, loc, dim, 1.0, d_slab, loc, rep_t, 1, 0.0, d_out, 1)
-        ctx.d2h(h_out, d_out, out_count * s, 2)
-        ctx.sync()
 
-    for _ in range(warmup):
-        step()
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    team = blob.Team(rank=rank, world=world, device=local)
+    team.attach_flags(exchange)
+    ctx = team.ctx()
+    AL = blob.OFFLOAD_ALWAYS
+    R, C_, G, U, D = blob.MG_REPLICATE, blob.MG_COMPUTE, blob.MG_GATHER, blob.MG_UPLOAD, blob.MG_DOWNLOAD
+
+    if kind == "gemm":
+        m = n = k = dim
+        j0, nc = blob.mg_partition(n, world, rank, 128)
+        k0, kk = blob.mg_partition(k, world, rank, 32)
+        hA, dA_unused = ctx.alloc(AL, m * kk * s)        # host: my K-share of A
+        hB, dB = ctx.alloc(AL, k * nc * s)               # my column slab of B
+        hC, dC_slab = ctx.alloc(AL, m * nc * s)          # my column slab of C
+        host_fill(blob.host_view(hA, m * kk, dtype), 7.0, 100 + rank)
+        host_fill(blob.host_view(hB, k * nc, dtype), 3.0, 200 + rank)
+        blob.host_view(hC, m * nc, dtype)[:] = 0
+        dA = ctx.alloc_device(m * k * s)                 # my replica of all of A
+        A_rep = team.map_peers(dA, exchange)
+        C_full = ctx.alloc_device(m * n * s) if rank == 0 else None   # rank 0 gathers C
+        C_root = team.map_root(C_full, exchange)                      # every rank maps rank 0's buffer
+        dC = C_full + j0 * m * s if rank == 0 else dC_slab
+        if dtype == "f32":
+            ctx.sgemm_prepare(m, nc, k, m, k)
+        # resident state for `value`: my share of A in my replica, my slab of B
+        ctx.h2d(dA + k0 * m * s, hA, m * kk * s, 0)
+        ctx.h2d(dB, hB, k * nc * s, 1)
+        ctx.sync()
+        flops, nbytes = gemm_flops(m, nc, k), gemm_bytes(m, nc, k, s)
+        total_flops = gemm_flops(m, n, k)
+        step_dev = lambda: team.gemm(rank, dtype, world, m, nc, k, 1.0, A_rep, m, dB, k, 0.0, dC, m, R | C_ | G,
+                                     C_gather=C_root + j0 * m * s)
+        step_e2e = lambda: (team.gemm(rank, dtype, world, m, nc, k, 1.0, A_rep, m, dB, k, 0.0, dC_slab, m, U | R | C_ | D,
+                                      hA_share=hA, hB=hB, hC=hC), team.sync())
+        h2d, d2h = (m * k + k * n) * s, m * n * s        # whole job per step: A once (1/N per rank), all of B; all of C
+        exchange_bytes = (world - 1) * m * k * s + (m * n * s) * (world - 1) // world
+    else:
+        m = n = dim
+        r0, rc = blob.mg_partition(m, world, rank, 32)
+        x0, xn = blob.mg_partition(n, world, rank, 1)
+        hA, dA = ctx.alloc(AL, rc * n * s)               # my compact row block of A (ld = rc)
+        hx, dx_unused = ctx.alloc(AL, max(1, xn) * s)    # host: my share of x
+        hy, dy_blk = ctx.alloc(AL, rc * s)
+        host_fill(blob.host_view(hA, rc * n, dtype), 7.0, 100 + rank)
+        host_fill(blob.host_view(hx, xn, dtype), 3.0, 200 + rank)
+        dx = ctx.alloc_device(n * s)
+        x_rep = team.map_peers(dx, exchange)
+        y_full = ctx.alloc_device(m * s) if rank == 0 else None
+        y_root = team.map_root(y_full, exchange)
+        dy = y_full + r0 * s if rank == 0 else dy_blk
+        ctx.h2d(dA, hA, rc * n * s, 0)
+        ctx.h2d(dx + x0 * s, hx, xn * s, 1)
+        ctx.sync()
+        flops, nbytes = gemv_flops(rc, n), gemv_bytes(rc, n, s)
+        total_flops = gemv_flops(m, n)
+        step_dev = lambda: team.gemv(rank, dtype, world, rc, n, 1.0, dA, rc, x_rep, 0.0, dy, R | C_ | G,
+                                     y_gather=y_root + r0 * s)
+        step_e2e = lambda: (team.gemv(rank, dtype, world, rc, n, 1.0, dA, rc, x_rep, 0.0, dy_blk, U | R | C_ | D,
+                                      hA=hA, h_lda=rc, hx_share=hx, hy=hy), team.sync())
+        h2d, d2h = (m * n + n) * s, m * s
+        exchange_bytes = (world - 1) * n * s + m * s * (world - 1) // world
+
+    # ---- value: device resident, the exchange inside the step ---------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, launches = time_device(ctx, step_dev, args.steps, args.warmup, barrier)
+    team.sync()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = max_over_ranks(ms)
+    kernel_name = ctx.last_kernel()
+    value = total_flops * args.steps / (ms * 1e-3) * 1e-9
+    per_gpu_gflops = flops * args.steps / (ms * 1e-3) * 1e-9
+    per_gpu_gbs = nbytes * args.steps / (ms * 1e-3) * 1e-9
+
+    # ---- e2e: host buffers, copies inside the timed region --------------------------------------
+    e2e_steps = max(1, min(args.steps, 5))
+    step_e2e()
     barrier()
     l0 = ctx.launch_count()
     t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
+    for _ in range(e2e_steps):
+        step_e2e()
     barrier()
-    dt = time.perf_counter() - t0
-    launches = ctx.launch_count() - l0
-    ctx.free(md, h_share, _d)
-    ctx.free(md, h_slab, d_slab)
-    ctx.free(md, h_out, d_out)
-    h2d = (share + slab_count) * world * s       # whole job: the replicated operand once + every slab
-    return {"seconds": dt, "h2d": h2d, "d2h": out_count * s * world, "launches": launches}
+    e_sec = max_over_ranks(time.perf_counter() - t0)
+    e2e_launches = ctx.launch_count() - l0
+    e2e_value = total_flops * e2e_steps / e_sec * 1e-9
+
+    # ---- parity of the sharded result at FULL size: one sampled block of my slab, recomputed in
+    # float64 from the host operands (rows of A are gathered from every rank's share)
+    bs = 16
+    if kind == "gemm":
+        i0, c0 = m // 2 + 5, nc // 2
+        mine = np.ascontiguousarray(blob.host_view(hA, m * kk, dtype).reshape(kk, m)[:, i0:i0 + bs]).astype(np.float64)
+        a_rows = np.concatenate(exchange(mine), axis=0)   # (k, bs): rows i0.. of A, every rank's K-share in K order
+        b_cols = blob.host_view(hB, k * nc, dtype).reshape(nc, k)[c0:c0 + bs].astype(np.float64)   # (bs, k)
+        want = b_cols @ a_rows                            # [col][row] = the column-major block
+        got = blob.host_view(hC, m * nc, dtype).reshape(nc, m)[c0:c0 + bs, i0:i0 + bs].astype(np.float64)
+    else:
+        xs = exchange(blob.host_view(hx, xn, dtype).astype(np.float64))
+        x_all = np.concatenate(xs)
+        i0 = rc // 2
+        want = blob.host_view(hA, rc * n, dtype).reshape(n, rc)[:, i0:i0 + bs].astype(np.float64).T @ x_all
+        got = blob.host_view(hy, rc, dtype)[i0:i0 + bs].astype(np.float64)
+    err = float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-300)))
+    errs = exchange(err)
+    parity = {"max_rel_err_sampled_blocks": max(errs), "tolerance": TOL[dtype], "ok": bool(max(errs) <= TOL[dtype]),
+              "what": f"one {bs}-wide block of every rank's slab of the e2e result vs a float64 recomputation from the host operands"}
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        roofline = kernel_roofline(ctx, peaks, peak_src, kind, dtype, per_gpu_gflops, per_gpu_gbs, kernel_name, flops, nbytes)
+        roofline["note"] = "per GPU: this rank's slab of the problem over the step time (max over ranks), exchange included"
+        line = {
+            "metric": f"{prefix(dtype).upper()}{kind.upper()} GFLOP/s (GPU-BLOB formula)",
+            "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": dtype, "data": "synthetic", "config": workload_config(kind, dtype, dim, world, True),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "GFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "ms_per_step": e_sec / e2e_steps * 1e3, "path": e2e_path(kind, dtype, world),
+                    "gpu_launches": e2e_launches},
+            "gpu_launches": launches,
+            "exchange": {"nvlink_bytes_per_step": exchange_bytes, "inside_timed_step": True,
+                         "how": "copy-engine pushes of each rank's share into every peer's replica + epoch flags "
+                                "(csrc/mg.cu); the consumer's compute stream waits per chunk (cuStreamWaitValue32)"},
+            "parity": parity,
+            "roofline": roofline,
+            "cpu_baseline": None,
+            "kernel": kernel_name,
+        }
+        print(json.dumps(line), flush=True)
+    barrier()
+    team.close()
 
 
-def run_own_arm(args, kind, dtype, dim):
+def run_weak(args, kind, dtype, dim, torch, dist, blob, rank, world, local):
+    """N > 1, --weak: independent per-GPU problems (round 1's layout, no exchange in the step)."""
+    ctx = blob.Context(local)
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    a, b, c = device_inputs(torch, kind, dtype, dim, seed=1 + rank)
+    torch.cuda.synchronize()
+    if kind == "gemm":
+        call = lambda: ctx.gemm(dtype, dim, dim, dim, 1.0, a, dim, b, dim, 0.0, c, dim)
+        flops = gemm_flops(dim, dim, dim)
+    else:
+        call = lambda: ctx.gemv(dtype, dim, dim, 1.0, a, dim, b, 1, 0.0, c, 1)
+        flops = gemv_flops(dim, dim)
+    ms, launches = time_device(ctx, call, args.steps, args.warmup, barrier)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    if rank == 0:
+        print(json.dumps({
+            "metric": f"{prefix(dtype).upper()}{kind.upper()} GFLOP/s (GPU-BLOB formula)",
+            "value": flops * world * args.steps / (ms * 1e-3) * 1e-9, "unit": "GFLOP/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+            "config": workload_config(kind, dtype, dim, world, False), "gpu_launches": launches,
+            "kernel": ctx.last_kernel()}), flush=True)
+    ctx.close()
+
+
+def run_own_arm(args, kind, dtype, dim, strong):
     import torch
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -394,153 +711,18 @@ def run_own_arm(args, kind, dtype, dim):
         raise SystemExit("bench.py: no CUDA device -- the B200 backend has no CPU path "
                          "(use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     blob = importlib.import_module("gpu-blas-offload-benchmark_b200")
-    ctx = blob.Context(local)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    # --- headline: device resident ---------------------------------------
-    loc = dim // world if (args.strong and world > 1) else dim
-    a, b, c = device_inputs(torch, kind, dtype, dim, seed=1 + rank if kind == "gemv" else 1, loc=loc)
-    if world > 1:
-        # the replicated operand travels over NVLink once (A for GEMM, x for GEMV);
-        # the slab operands (B, C columns / A, y rows) are generated per rank
-        rep = a if kind == "gemm" else b
-        dist.broadcast(rep, src=0)
-        if kind == "gemm":
-            g = torch.Generator(device="cuda").manual_seed(100 + rank)
-            b = torch.randint(0, 100, (dim * loc,), generator=g, device="cuda").to(b.dtype) / 3.0
-    torch.cuda.synchronize()
-    if kind == "gemm":
-        call = lambda: ctx.gemm(dtype, dim, loc, dim, 1.0, a, dim, b, dim, 0.0, c, dim)
-        flops, nbytes = gemm_flops(dim, loc, dim), gemm_bytes(dim, loc, dim, ELEM[dtype])
-    else:
-        call = lambda: ctx.gemv(dtype, loc, dim, 1.0, a, loc, b, 1, 0.0, c, 1)
-        flops, nbytes = gemv_flops(loc, dim), gemv_bytes(loc, dim, ELEM[dtype])
-
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    ms, launches = time_device(ctx, call, args.steps, args.warmup, barrier)
-    clocks = sampler.stop() if rank == 0 else None
-    ms = max_over_ranks(ms)
-    kernel_name = ctx.last_kernel()
-    value = flops * world * args.steps / (ms * 1e-3) * 1e-9
-    per_gpu_gflops = flops * args.steps / (ms * 1e-3) * 1e-9
-    per_gpu_gbs = nbytes * args.steps / (ms * 1e-3) * 1e-9
-    del a, b, c
-    torch.cuda.empty_cache()
-
-    # --- e2e through the plugin path with host buffers ---------------------
-    e2e_steps = max(1, min(args.steps, 5))
     if world == 1:
-        e = bench_e2e(blob, ctx, kind, dtype, dim, e2e_steps, 1, barrier)
-    else:
-        e = bench_e2e_multi(blob, ctx, torch, dist, kind, dtype, dim, e2e_steps, 1, barrier, rank, world, loc)
-    e_sec = max_over_ranks(e["seconds"])
-    e2e_value = flops * world * e2e_steps / e_sec * 1e-9
-
-    if rank != 0:
-        ctx.close()
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
+        run_single(args, kind, dtype, dim, torch, blob, local)
         return
-
-    # --- roofline of the dominant kernel -----------------------------------
-    peaks, peak_src = measured_peaks()
-    if kind == "gemm" and dtype == "f64":
-        pk = ctx.probe_peak("dmma")  # GFLOP/s, measured live on this GPU
-        pk2 = ctx.probe_peak("dfma")
-        peak = max(pk, pk2)
-        roofline = {"bound": "tensor", "achieved": per_gpu_gflops / 1e3, "peak": peak / 1e3, "unit": "TFLOP/s",
-                    "frac": per_gpu_gflops / peak, "traffic": None, "kernel": kernel_name,
-                    "peak_source": "FP64 tensor (DMMA) pipe: b200_probe_peak(dmma) measured live on this GPU; "
-                                   "MEASURED_PEAKS.json holds no FP64 peak",
-                    "probe_dfma_tflops": pk2 / 1e3, "probe_dmma_tflops": pk / 1e3}
-    elif kind == "gemm":
-        # 3xTF32: three tensor-core MMAs per FP32 product.  TF32 runs at half the bf16 rate, so the
-        # measured denominator is MEASURED_PEAKS bf16_tflops / 2 / 3.
-        ffma = ctx.probe_peak("ffma")
-        tc_kernel = "tcgen05" in kernel_name
-        peak = peaks["bf16_tflops"] * 1e3 / 2.0 / 3.0 if tc_kernel else ffma
-        roofline = {"bound": "tensor" if tc_kernel else "fp32-pipe", "achieved": per_gpu_gflops / 1e3,
-                    "peak": peak / 1e3, "unit": "TFLOP/s", "frac": per_gpu_gflops / peak, "traffic": None,
-                    "kernel": kernel_name,
-                    "peak_source": (f"bf16_tflops of {peak_src} / 2 (TF32 = half the bf16 tensor rate) / 3 "
-                                    "(3xTF32: three MMAs per FP32 product)") if tc_kernel else
-                                   "b200_probe_peak(ffma) measured live on this GPU",
-                    "probe_ffma_tflops": ffma / 1e3, "frac_of_ffma_peak": per_gpu_gflops / ffma}
-    else:
-        roofline = {"bound": "hbm", "achieved": per_gpu_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": per_gpu_gbs / peaks["hbm_gbs"], "traffic": None, "kernel": kernel_name,
-                    "peak_source": f"hbm_gbs of {peak_src} (burst copy figure)"}
-
-    traffic, traffic_src = ncu_traffic(args.workload, kernel_name) if (world == 1 and dim == default_dim(kind)) else (None, None)
-    roofline["traffic"] = traffic
-    roofline["traffic_source"] = traffic_src
-    roofline["algorithmic_bytes"] = nbytes
-    roofline["algorithmic_flops"] = flops
-
-    # --- the other three kernels at their headline sizes (explanatory) ------
-    extras = {}
-    if not args.no_extras and world == 1:
-        for (k2, d2, n2) in (("gemm", "f64", 8192), ("gemm", "f32", 8192), ("gemv", "f64", 32768), ("gemv", "f32", 32768)):
-            if (k2, d2, n2) == (kind, dtype, dim):
-                continue
-            r = bench_kernel(blob, ctx, torch, k2, d2, n2, max(3, min(args.steps, 10)), 3)
-            key = f"{'d' if d2 == 'f64' else 's'}{k2}_{n2}"
-            extras[key] = {"gflops": round(r["gflops"], 1), "ms": round(r["ms_per_step"], 4), "kernel": r["kernel"]}
-            if k2 == "gemv":
-                extras[key]["gbs"] = round(r["gbs"], 1)
-                extras[key]["hbm_frac"] = round(r["gbs"] / peaks["hbm_gbs"], 3)
-            torch.cuda.empty_cache()
-        try:
-            extras["probe_ffma_tflops"] = round(ctx.probe_peak("ffma") / 1e3, 2)
-            extras["probe_copy_gbs"] = round(ctx.probe_peak("copy"), 1)
-        except Exception as ex:  # noqa: BLE001 -- explanatory only
-            extras["probe_error"] = str(ex)
-
-    # --- CPU baseline: the reference's OpenBLAS path on this box's cores -----
-    cpu = time_reference(kind, dtype, dim, 3, 1)
-
-    line = {
-        "metric": f"{'D' if dtype == 'f64' else 'S'}{kind.upper()} GFLOP/s (GPU-BLOB formula)",
-        "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if (args.strong and world > 1) else "weak", "vs_baseline": None,
-        "dtype": dtype, "data": "synthetic", "config": workload_config(kind, dtype, dim, world, args.strong),
-        "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "GFLOP/s", "h2d_bytes_per_step": e["h2d"],
-                "d2h_bytes_per_step": e["d2h"], "steps": e2e_steps,
-                "path": ("b200_%sgem%s_offload (Always mode of gpu::gem%s_gpu<T>), pinned host buffers"
-                         % ("d" if dtype == "f64" else "s", "m" if kind == "gemm" else "v", "m" if kind == "gemm" else "v"))
-                if world == 1 else
-                ("per rank and step: b200_h2d_async of its 1/N share of the replicated operand + its slab from "
-                 "pinned host buffers, NCCL all-gather over NVLink, b200_%sgem%s, b200_d2h_async of its result slab"
-                 % ("d" if dtype == "f64" else "s", "m" if kind == "gemm" else "v"))},
-        "gpu_launches": launches,
-        "roofline": roofline,
-        "cpu_baseline": {"value": cpu["value"], "unit": "GFLOP/s", "cores": cpu["cores"], "kind": cpu["kind"],
-                         "sample": cpu["sample"]},
-        "kernel": kernel_name,
-        "extras": extras,
-    }
-    print(json.dumps(line), flush=True)
-    ctx.close()
-    if world > 1:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    try:
+        if strong:
+            run_team(args, kind, dtype, dim, torch, dist, blob, rank, world, local)
+        else:
+            run_weak(args, kind, dtype, dim, torch, dist, blob, rank, world, local)
         dist.barrier()
+    finally:
         dist.destroy_process_group()
 
 
@@ -557,17 +739,20 @@ def main():
     ap.add_argument("--workload", default="dgemm", choices=["dgemm", "sgemm", "dgemv", "sgemv"])
     ap.add_argument("--dim", type=int, default=0)
     ap.add_argument("--no-extras", action="store_true")
-    ap.add_argument("--strong", action="store_true",
-                    help="N > 1: partition ONE dim^3 (dim^2) problem across the GPUs (BASELINE config 5) instead of weak scaling")
+    ap.add_argument("--strong", action="store_true", help="(default at N > 1) partition ONE problem across the GPUs")
+    ap.add_argument("--weak", action="store_true",
+                    help="N > 1: independent per-GPU problems of the N = 1 size instead of BASELINE config 5")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     kind = "gemm" if args.workload.endswith("gemm") else "gemv"
     dtype = "f64" if args.workload[0] == "d" else "f32"
-    dim = args.dim or default_dim(kind)
+    world = max(args.gpus, int(os.environ.get("WORLD_SIZE", "1")))
+    strong = world > 1 and not args.weak
+    dim = args.dim or (STRONG_DIM if strong else default_dim(kind))
     if args.impl == "reference":
-        run_reference_arm(args, kind, dtype, dim)
+        run_reference_arm(args, kind, dtype, dim, strong)
     else:
-        run_own_arm(args, kind, dtype, dim)
+        run_own_arm(args, kind, dtype, dim, strong)
 
 
 if __name__ == "__main__":

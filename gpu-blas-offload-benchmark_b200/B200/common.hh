@@ -10,6 +10,7 @@
 
 #include <cstdlib>
 #include <iostream>
+#include <string>
 
 #include <b200blas.h>
 
@@ -62,6 +63,45 @@ class context_holder {
 
  private:
   b200_ctx* ctx_ = nullptr;
+};
+
+/** Number of GPUs one problem is partitioned over: environment variable B200_NGPUS
+ * (default 1).  The reference has no multi-GPU notion; this is read where it reads its
+ * single device (cuBLAS/gemm.hh:45-63, cuBLAS/gemv.hh:45-60). */
+inline int ngpus() {
+  static const int n = [] {
+    const char* e = std::getenv("B200_NGPUS");
+    const int v = e ? std::atoi(e) : 1;
+    return v > 1 ? v : 1;
+  }();
+  return n;
+}
+
+/** B200_UPLOAD_C=1: upload C / y in Once and Always mode even though beta == 0 makes it dead
+ * traffic, exactly as the reference does (cuBLAS/gemm.hh:104-105,130-131,
+ * cuBLAS/gemv.hh:100-101,126-127) -- for like-for-like transfer volumes against the cuBLAS
+ * backend.  Default: skipped.  (The library reads the same variable for Always mode.) */
+inline bool upload_c() {
+  static const bool v = [] {
+    const char* e = std::getenv("B200_UPLOAD_C");
+    return e != nullptr && std::string(e) != "0" && std::string(e) != "off";
+  }();
+  return v;
+}
+
+/** Lazily created team of `ngpus()` devices (one per backend object, like the context). */
+class team_holder {
+ public:
+  ~team_holder() {
+    if (mg_ != nullptr) b200CheckError(b200_mg_destroy(mg_));
+  }
+  b200_mg* get() {
+    if (mg_ == nullptr) b200CheckError(b200_mg_create(&mg_, ngpus()));
+    return mg_;
+  }
+
+ private:
+  b200_mg* mg_ = nullptr;
 };
 
 }  // namespace b200detail

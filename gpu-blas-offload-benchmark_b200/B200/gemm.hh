@@ -12,6 +12,10 @@
 //   always    -                       b200_?gemm_offload: slabbed   -
 //                                     H2D || compute || D2H, sync
 //   unified   advise + prefetch ->GPU b200_?gemm on managed ptrs    prefetch C ->CPU, sync
+//
+// B200_NGPUS=G (> 1) partitions every problem over a team of G GPUs through the same five
+// virtuals (b200_mg_problem_*): column slabs of B and C, A uploaded 1/G per GPU over its own
+// PCIe link and replicated over NVLink while the GEMM runs (csrc/mg.cu).
 #ifdef GPU_B200
 
 #include <algorithm>
@@ -43,8 +47,18 @@ class gemm_gpu : public gemm<T> {
     m_ = m;
     n_ = n;
     k_ = k;
-    b200_ctx* ctx = ctx_.get();
     const int mode = static_cast<int>(offload_);
+    if (b200detail::ngpus() > 1) {
+      void *h0 = nullptr, *h1 = nullptr, *h2 = nullptr;
+      b200CheckError(b200_mg_problem_create(team_.get(), B200_MG_GEMM, (int)sizeof(T), mode, m_, n_, k_,
+                                            &h0, &h1, &h2, &problem_));
+      A_ = static_cast<T*>(h0);
+      B_ = static_cast<T*>(h1);
+      C_ = static_cast<T*>(h2);
+      initInputMatrices();
+      return;
+    }
+    b200_ctx* ctx = ctx_.get();
     a_.acquire(ctx, mode, (size_t)m_ * k_);
     b_.acquire(ctx, mode, (size_t)k_ * n_);
     c_.acquire(ctx, mode, (size_t)m_ * n_);
@@ -56,18 +70,25 @@ class gemm_gpu : public gemm<T> {
       b200CheckError(b200_advise(ctx, b_.dev, b_.bytes, 1));
       b200CheckError(b200_advise(ctx, c_.dev, c_.bytes, 0));
     }
+    if constexpr (std::is_same_v<T, float>)
+      b200CheckError(b200_sgemm_prepare(ctx, m_, n_, k_, std::max(1, m_), std::max(1, k_)));
     initInputMatrices();
   }
 
  private:
   void preLoopRequirements() override {
+    if (problem_ != nullptr) {
+      b200CheckError(b200_mg_problem_preloop(problem_, (double)beta));
+      return;
+    }
     b200_ctx* ctx = ctx_.get();
     if (offload_ == gpuOffloadType::once) {
       b200CheckError(b200_h2d_async(ctx, a_.dev, a_.host, a_.bytes, 0));
       b200CheckError(b200_h2d_async(ctx, b_.dev, b_.host, b_.bytes, 1));
       // BLAS never reads the output operand when beta == 0, so the reference's
       // third upload (cuBLAS/gemm.hh:104-105, cuBLAS/gemv.hh:100-101) is skipped
-      if (beta != T(0)) b200CheckError(b200_h2d_async(ctx, c_.dev, c_.host, c_.bytes, 2));
+      // (B200_UPLOAD_C=1 restores it)
+      if (beta != T(0) || b200detail::upload_c()) b200CheckError(b200_h2d_async(ctx, c_.dev, c_.host, c_.bytes, 2));
     } else if (offload_ == gpuOffloadType::unified) {
       b200CheckError(b200_prefetch_async(ctx, a_.dev, a_.bytes, 1, 0));
       b200CheckError(b200_prefetch_async(ctx, b_.dev, b_.bytes, 1, 1));
@@ -76,6 +97,10 @@ class gemm_gpu : public gemm<T> {
   }
 
   void callGemm() override {
+    if (problem_ != nullptr) {
+      b200CheckError(b200_mg_problem_call(problem_, (double)alpha, (double)beta));
+      return;
+    }
     b200_ctx* ctx = ctx_.get();
     const int lda = std::max(1, m_), ldb = std::max(1, k_), ldc = std::max(1, m_);
     if (offload_ == gpuOffloadType::always) {
@@ -96,6 +121,10 @@ class gemm_gpu : public gemm<T> {
   }
 
   void postLoopRequirements() override {
+    if (problem_ != nullptr) {
+      b200CheckError(b200_mg_problem_postloop(problem_));
+      return;
+    }
     b200_ctx* ctx = ctx_.get();
     if (offload_ == gpuOffloadType::once) {
       b200CheckError(b200_d2h_async(ctx, c_.host, c_.dev, c_.bytes, 2));
@@ -107,6 +136,11 @@ class gemm_gpu : public gemm<T> {
   }
 
   void postCallKernelCleanup() override {
+    if (problem_ != nullptr) {
+      b200CheckError(b200_mg_problem_destroy(problem_));
+      problem_ = nullptr;
+      return;
+    }
     b200_ctx* ctx = ctx_.get();
     const int mode = static_cast<int>(offload_);
     a_.release(ctx, mode);
@@ -115,6 +149,8 @@ class gemm_gpu : public gemm<T> {
   }
 
   b200detail::context_holder ctx_;
+  b200detail::team_holder team_;        // B200_NGPUS > 1
+  b200_mg_problem* problem_ = nullptr;  // the current partitioned problem of the team
   b200detail::operand<T> a_, b_, c_;
   const T alpha = ALPHA;
   const T beta = BETA;

@@ -33,8 +33,18 @@ class gemv_gpu : public gemv<T> {
     offload_ = offload;
     m_ = m;
     n_ = n;
-    b200_ctx* ctx = ctx_.get();
     const int mode = static_cast<int>(offload_);
+    if (b200detail::ngpus() > 1) {  // row blocks of A and y over a team of GPUs, x replicated (csrc/mg.cu)
+      void *h0 = nullptr, *h1 = nullptr, *h2 = nullptr;
+      b200CheckError(b200_mg_problem_create(team_.get(), B200_MG_GEMV, (int)sizeof(T), mode, m_, n_, 0,
+                                            &h0, &h1, &h2, &problem_));
+      A_ = static_cast<T*>(h0);
+      x_ = static_cast<T*>(h1);
+      y_ = static_cast<T*>(h2);
+      initInputMatrixVector();
+      return;
+    }
+    b200_ctx* ctx = ctx_.get();
     a_.acquire(ctx, mode, (size_t)m_ * n_);
     x_op_.acquire(ctx, mode, (size_t)n_);
     y_op_.acquire(ctx, mode, (size_t)m_);
@@ -51,13 +61,18 @@ class gemv_gpu : public gemv<T> {
 
  private:
   void preLoopRequirements() override {
+    if (problem_ != nullptr) {
+      b200CheckError(b200_mg_problem_preloop(problem_, (double)beta));
+      return;
+    }
     b200_ctx* ctx = ctx_.get();
     if (offload_ == gpuOffloadType::once) {
       b200CheckError(b200_h2d_async(ctx, a_.dev, a_.host, a_.bytes, 0));
       b200CheckError(b200_h2d_async(ctx, x_op_.dev, x_op_.host, x_op_.bytes, 1));
       // BLAS never reads the output operand when beta == 0, so the reference's
       // third upload (cuBLAS/gemm.hh:104-105, cuBLAS/gemv.hh:100-101) is skipped
-      if (beta != T(0)) b200CheckError(b200_h2d_async(ctx, y_op_.dev, y_op_.host, y_op_.bytes, 2));
+      // (B200_UPLOAD_C=1 restores it)
+      if (beta != T(0) || b200detail::upload_c()) b200CheckError(b200_h2d_async(ctx, y_op_.dev, y_op_.host, y_op_.bytes, 2));
     } else if (offload_ == gpuOffloadType::unified) {
       b200CheckError(b200_prefetch_async(ctx, a_.dev, a_.bytes, 1, 0));
       b200CheckError(b200_prefetch_async(ctx, x_op_.dev, x_op_.bytes, 1, 1));
@@ -66,6 +81,10 @@ class gemv_gpu : public gemv<T> {
   }
 
   void callGemv() override {
+    if (problem_ != nullptr) {
+      b200CheckError(b200_mg_problem_call(problem_, (double)alpha, (double)beta));
+      return;
+    }
     b200_ctx* ctx = ctx_.get();
     const int lda = std::max(1, m_);
     if (offload_ == gpuOffloadType::always) {
@@ -86,6 +105,10 @@ class gemv_gpu : public gemv<T> {
   }
 
   void postLoopRequirements() override {
+    if (problem_ != nullptr) {
+      b200CheckError(b200_mg_problem_postloop(problem_));
+      return;
+    }
     b200_ctx* ctx = ctx_.get();
     if (offload_ == gpuOffloadType::once) {
       b200CheckError(b200_d2h_async(ctx, y_op_.host, y_op_.dev, y_op_.bytes, 2));
@@ -97,6 +120,11 @@ class gemv_gpu : public gemv<T> {
   }
 
   void postCallKernelCleanup() override {
+    if (problem_ != nullptr) {
+      b200CheckError(b200_mg_problem_destroy(problem_));
+      problem_ = nullptr;
+      return;
+    }
     b200_ctx* ctx = ctx_.get();
     const int mode = static_cast<int>(offload_);
     a_.release(ctx, mode);
@@ -105,6 +133,8 @@ class gemv_gpu : public gemv<T> {
   }
 
   b200detail::context_holder ctx_;
+  b200detail::team_holder team_;        // B200_NGPUS > 1
+  b200_mg_problem* problem_ = nullptr;  // the current partitioned problem of the team
   b200detail::operand<T> a_, x_op_, y_op_;
   const T alpha = ALPHA;
   const T beta = BETA;

@@ -129,17 +129,32 @@ def build_harness(force=False):
     try:
         tree = os.path.join(scratch, "tree")
         reg.make_overlay(REFERENCE, tree, os.path.join(PKG, "B200"))
-        shutil.copy(consume, os.path.join(LIBDIR, "libconsume.so"))
         sp = subprocess.check_output(
             [sys.executable, "-c", "import scipy,os;print(os.path.dirname(os.path.dirname(scipy.__file__)))"],
             text=True).strip()
         scipy_libs = os.path.join(sp, "scipy.libs")
         openblas = [os.path.join(scipy_libs, f) for f in os.listdir(scipy_libs) if f.startswith("libscipy_openblas")][0]
+        # ---- the harness: the reference's own build entry point on the overlay,
+        #   make COMPILER=GNU CPU_LIB=OPENBLAS GPU_LIB=B200 CXXFLAGS="-I.. -L.. -Wl,-rpath,.."
+        # (reference Makefile:44-60,155-159,167-226).  Two command-line overrides, both about WHERE
+        # the binary runs, not what it is: CXXFLAGS_GNU swaps -march=native for x86-64-v3 (built in a
+        # CPU container, run on the GPU box), and the rpath is $ORIGIN so lib/ is self-contained.
+        shim = os.path.join(scratch, "shim")
+        os.makedirs(shim)
+        os.symlink(openblas, os.path.join(shim, "libopenblas.so"))
+        gfortran = [os.path.join(scipy_libs, f) for f in os.listdir(scipy_libs) if f.startswith("libgfortran")][0]
+        os.symlink(gfortran, os.path.join(shim, "libgfortran.so"))
+        cxxflags = " ".join(["-I" + os.path.join(ROOT, "oracle", "cblas_shim"), "-L" + shim,
+                             "-Wl,-rpath," + scipy_libs, "-I" + os.path.join(ROOT, "include"), "-L" + LIBDIR,
+                             "-Wl,-rpath,\\$$ORIGIN"])
+        out = _run(["make", "-C", tree, "COMPILER=GNU", "CPU_LIB=OPENBLAS", "GPU_LIB=B200",
+                    "CXXFLAGS_GNU=-std=c++17 -Wall -Ofast -march=x86-64-v3", "CXXFLAGS=" + cxxflags])
+        with open(os.path.join(LIBDIR, "harness_make.log"), "w") as f:
+            f.write(out)
+        shutil.copy(os.path.join(tree, "gpu-blob"), blob)
+        shutil.copy(os.path.join(tree, "src", "Consume", "libconsume.so"), os.path.join(LIBDIR, "libconsume.so"))
         common = ["-std=c++17", "-Wall", "-march=x86-64-v3", "-DGPU_B200", "-I" + os.path.join(ROOT, "include")]
         link = ["-L" + LIBDIR, "-lb200blas", "-Wl,-rpath,$ORIGIN"]
-        _run(["g++", os.path.join(tree, "src", "main.cc"), "-Ofast", "-DCPU_OPENBLAS",
-              "-I" + os.path.join(ROOT, "oracle", "cblas_shim")] + common +
-             [openblas, "-lpthread", "-Wl,-rpath," + scipy_libs, "-lconsume", "-lm"] + link + ["-o", blob])
         _run(["g++", os.path.join(PKG, "harness", "parity_driver.cc"), "-O2", "-I" + tree] + common + link +
              ["-o", parity])
     finally:

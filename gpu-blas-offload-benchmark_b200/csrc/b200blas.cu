@@ -126,6 +126,87 @@ static size_t live_pop(std::vector<CachedBlock>& v, void* p, void** alias = null
   return 0;
 }
 
+// cudaMemPrefetchAsync / cudaMemAdvise take a cudaMemLocation from CUDA 13 on (the 4-argument
+// forms the reference uses, cuBLAS/gemm.hh:110-115,212-213, are gone there); 12.2+ has the
+// same thing as *_v2.  device < 0 selects the CPU.
+cudaError_t mem_prefetch(const void* p, size_t bytes, int device, cudaStream_t s) {
+#if CUDART_VERSION >= 12020
+  cudaMemLocation loc;
+  loc.type = device < 0 ? cudaMemLocationTypeHost : cudaMemLocationTypeDevice;
+  loc.id = device < 0 ? 0 : device;
+#if CUDART_VERSION >= 13000
+  return cudaMemPrefetchAsync(p, bytes, loc, 0, s);
+#else
+  return cudaMemPrefetchAsync_v2(p, bytes, loc, 0, s);
+#endif
+#else
+  return cudaMemPrefetchAsync(p, bytes, device < 0 ? cudaCpuDeviceId : device, s);
+#endif
+}
+
+cudaError_t mem_advise(const void* p, size_t bytes, cudaMemoryAdvise advice, int device) {
+#if CUDART_VERSION >= 12020
+  cudaMemLocation loc;
+  loc.type = device < 0 ? cudaMemLocationTypeHost : cudaMemLocationTypeDevice;
+  loc.id = device < 0 ? 0 : device;
+#if CUDART_VERSION >= 13000
+  return cudaMemAdvise(p, bytes, advice, loc);
+#else
+  return cudaMemAdvise_v2(p, bytes, advice, loc);
+#endif
+#else
+  return cudaMemAdvise(p, bytes, advice, device < 0 ? cudaCpuDeviceId : device);
+#endif
+}
+
+// Free every cached (idle) block of this context: called when an allocation fails so that
+// a long sweep does not die with most of HBM sitting in idle caches.
+static void trim_caches(b200_ctx* ctx) {
+  for (auto& b : ctx->pinned_cache) cudaFreeHost(b.ptr);
+  for (auto& b : ctx->device_cache) cudaFree(b.ptr);
+  for (auto& b : ctx->managed_cache) cudaFree(b.ptr);
+  ctx->pinned_cache.clear();
+  ctx->device_cache.clear();
+  ctx->managed_cache.clear();
+  cudaGetLastError();
+}
+
+static int take_device_block(b200_ctx* ctx, size_t cap, void** out) {
+  void* d = cache_take(ctx->device_cache, cap);
+  if (!d) {
+    cudaError_t e = cudaMalloc(&d, cap);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      trim_caches(ctx);
+      e = cudaMalloc(&d, cap);
+    }
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      set_error("b200_alloc: cudaMalloc(%zu) -> %s", cap, cudaGetErrorString(e));
+      return 1;
+    }
+  }
+  *out = d;
+  return 0;
+}
+
+int alloc_device(b200_ctx* ctx, size_t bytes, void** dev) {
+  const size_t cap = round_capacity(bytes ? bytes : 1);
+  if (take_device_block(ctx, cap, dev)) return 1;
+  ctx->live_dev.push_back({*dev, cap});
+  return 0;
+}
+
+int free_device(b200_ctx* ctx, void* dev) {
+  if (!dev) return 0;
+  const size_t cap = live_pop(ctx->live_dev, dev);
+  if (cap)
+    cache_put(ctx->device_cache, dev, cap, (size_t)48 << 30, [](void* p) { cudaFree(p); });
+  else
+    B200_CUDA(cudaFree(dev));
+  return 0;
+}
+
 // Device-side address of a pinned host pointer handed out by b200_alloc (nullptr if the
 // pointer is not ours -- then the zero-copy path is not taken).
 static void* device_alias(const b200_ctx* ctx, const void* host) {
@@ -170,6 +251,11 @@ int b200_ctx_create(b200_ctx** out, int device) {
   B200_REQUIRE(prop.major == 10, "b200_ctx_create: device %d is sm_%d%d; this build is sm_100a only",
                device, prop.major, prop.minor);
   b200_ctx* ctx = new b200_ctx();
+  // any failure below destroys what has been created so far
+  struct Guard {
+    b200_ctx* c;
+    ~Guard() { if (c) b200_ctx_destroy(c); }
+  } guard{ctx};
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
   ctx->l2_bytes = (size_t)prop.l2CacheSize;
@@ -191,9 +277,15 @@ int b200_ctx_create(b200_ctx** out, int device) {
   if (const char* e = getenv("B200_DGEMM_TMA")) ctx->opt_dgemm_tma = strcmp(e, "off") != 0 && strcmp(e, "0") != 0;
   if (const char* e = getenv("B200_DGEMM_STREAMK")) ctx->opt_dgemm_streamk = strcmp(e, "off") != 0 && strcmp(e, "0") != 0;
   if (const char* e = getenv("B200_DGEMM_TILE")) ctx->opt_dgemm_tile = (atoi(e) == 32 || atoi(e) == 64 || atoi(e) == 128) ? atoi(e) : 0;
+  if (const char* e = getenv("B200_UPLOAD_C")) ctx->opt_upload_c = strcmp(e, "0") != 0 && strcmp(e, "off") != 0;
   ctx->num_counters = 1 << 16;
   B200_CUDA(cudaMalloc((void**)&ctx->counters, ctx->num_counters * sizeof(unsigned int)));
   B200_CUDA(cudaMemset(ctx->counters, 0, ctx->num_counters * sizeof(unsigned int)));
+  // Scratch for split-K / split-N / stream-K partial tiles (<= ~56 MB whatever the problem
+  // size) is reserved here, once, like cuBLAS reserves its workspace in cublasCreate;
+  // b200_sgemm_prepare adds the 3xTF32 operand splits for one SGEMM shape.
+  if (ensure_workspace(ctx, (size_t)96 << 20)) return 1;
+  guard.c = nullptr;
   *out = ctx;
   return 0;
 }
@@ -201,7 +293,9 @@ int b200_ctx_create(b200_ctx** out, int device) {
 int b200_ctx_destroy(b200_ctx* ctx) {
   if (!ctx) return 0;
   cudaSetDevice(ctx->device);
-  cudaDeviceSynchronize();
+  if (ctx->own_compute) cudaStreamSynchronize(ctx->own_compute);
+  for (int l = 0; l < B200_NUM_LANES; l++)
+    if (ctx->lane[l]) cudaStreamSynchronize(ctx->lane[l]);
   for (auto& b : ctx->pinned_cache) cudaFreeHost(b.ptr);
   for (auto& b : ctx->device_cache) cudaFree(b.ptr);
   for (auto& b : ctx->managed_cache) cudaFree(b.ptr);
@@ -268,6 +362,12 @@ int b200_ctx_set_option(b200_ctx* ctx, const char* key, const char* value) {
     else B200_REQUIRE(false, "b200_ctx_set_option: dgemm_tma must be on|off, got '%s'", value);
     return 0;
   }
+  if (!strcmp(key, "upload_c")) {
+    if (!strcmp(value, "on") || !strcmp(value, "1")) ctx->opt_upload_c = 1;
+    else if (!strcmp(value, "off") || !strcmp(value, "0")) ctx->opt_upload_c = 0;
+    else B200_REQUIRE(false, "b200_ctx_set_option: upload_c must be on|off, got '%s'", value);
+    return 0;
+  }
   B200_REQUIRE(false, "b200_ctx_set_option: unknown key '%s'", key);
   return 0;
 }
@@ -287,38 +387,43 @@ int b200_alloc(b200_ctx* ctx, int mode, size_t bytes, void** host, void** dev) {
     // managed blocks are pooled too: cudaMallocManaged / cudaFree churn leaves
     // asynchronous UVM driver work (unmap, page-table teardown) that lands in the
     // next timed region
-    if (ensure_workspace(ctx, std::min<size_t>(4 * bytes + ((size_t)96 << 20), (size_t)24 << 30))) return 1;
     const size_t cap = round_capacity_managed(bytes);
     void* p = cache_take(ctx->managed_cache, cap);
-    if (!p) B200_CUDA(cudaMallocManaged(&p, cap, cudaMemAttachGlobal));
+    if (!p) {
+      cudaError_t e = cudaMallocManaged(&p, cap, cudaMemAttachGlobal);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        trim_caches(ctx);
+        B200_CUDA(cudaMallocManaged(&p, cap, cudaMemAttachGlobal));
+      }
+    }
     ctx->live_managed.push_back({p, cap});
     *host = *dev = p;
     return 0;
   }
   B200_REQUIRE(mode == B200_OFFLOAD_ALWAYS || mode == B200_OFFLOAD_ONCE,
                "b200_alloc: unknown offload mode %d", mode);
-  // Grow the scratch workspace here, where the harness is not timing: the 3xTF32
-  // operand splits need 2 x (|A| + |B|), split-K / stream-K partial tiles at most ~56 MB.
-  if (ensure_workspace(ctx, std::min<size_t>(4 * bytes + ((size_t)96 << 20), (size_t)24 << 30))) return 1;
   const size_t cap = round_capacity(bytes);
   void* alias = nullptr;
   void* h = cache_take(ctx->pinned_cache, cap, &alias);
   if (!h) {
-    B200_CUDA(cudaMallocHost(&h, cap));
+    cudaError_t e = cudaMallocHost(&h, cap);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      trim_caches(ctx);
+      B200_CUDA(cudaMallocHost(&h, cap));
+    }
     // under UVA pinned memory is mapped into the device address space (zero-copy path)
     if (cudaHostGetDevicePointer(&alias, h, 0) != cudaSuccess) {
       alias = nullptr;
       cudaGetLastError();
     }
   }
-  void* d = cache_take(ctx->device_cache, cap);
-  if (!d) {
-    cudaError_t e = cudaMalloc(&d, cap);
-    if (e != cudaSuccess) {
-      cudaFreeHost(h);
-      set_error("b200_alloc: cudaMalloc(%zu) -> %s", cap, cudaGetErrorString(e));
-      return 1;
-    }
+  void* d = nullptr;
+  if (take_device_block(ctx, cap, &d)) {
+    // keep the pinned block (it may have come from the cache) for the next attempt
+    cache_put(ctx->pinned_cache, h, cap, (size_t)6 << 30, [](void* p) { cudaFreeHost(p); }, alias);
+    return 1;
   }
   ctx->live_host.push_back({h, cap, alias});
   ctx->live_dev.push_back({d, cap});
@@ -361,6 +466,20 @@ int b200_free(b200_ctx* ctx, int mode, void* host, void* dev) {
   return 0;
 }
 
+int b200_alloc_device(b200_ctx* ctx, size_t bytes, void** dev) {
+  B200_REQUIRE(ctx && dev, "b200_alloc_device: null argument");
+  *dev = nullptr;
+  B200_CUDA(cudaSetDevice(ctx->device));
+  return alloc_device(ctx, bytes, dev);
+}
+
+int b200_free_device(b200_ctx* ctx, void* dev) {
+  B200_REQUIRE(ctx, "b200_free_device: null context");
+  if (ctx->compute_dirty || ctx->lane_dirty[0] || ctx->lane_dirty[1] || ctx->lane_dirty[2])
+    if (b200_sync(ctx)) return 1;
+  return free_device(ctx, dev);
+}
+
 int b200_h2d_async(b200_ctx* ctx, void* dev, const void* host, size_t bytes, int lane) {
   B200_REQUIRE(ctx && lane >= 0 && lane < B200_NUM_LANES, "b200_h2d_async: bad lane %d", lane);
   if (bytes == 0) return 0;
@@ -377,6 +496,10 @@ int b200_d2h_async(b200_ctx* ctx, void* host, const void* dev, size_t bytes, int
   if (bytes == 0) return 0;
   if (lanes_wait_for_compute(ctx)) return 1;
   B200_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->lane[lane]));
+  // a later kernel may overwrite `dev`: it must wait for this copy to have read it (the
+  // reference gets this from the legacy default stream)
+  B200_CUDA(cudaEventRecord(ctx->lane_done[lane], ctx->lane[lane]));
+  ctx->lane_pending[lane] = true;
   ctx->lane_dirty[lane] = true;
   return 0;
 }
@@ -385,12 +508,9 @@ int b200_prefetch_async(b200_ctx* ctx, const void* managed, size_t bytes, int to
   B200_REQUIRE(ctx && lane >= 0 && lane < B200_NUM_LANES, "b200_prefetch_async: bad lane %d", lane);
   if (bytes == 0) return 0;
   if (lanes_wait_for_compute(ctx)) return 1;
-  B200_CUDA(cudaMemPrefetchAsync(managed, bytes, to_device ? ctx->device : cudaCpuDeviceId,
-                                 ctx->lane[lane]));
-  if (to_device) {
-    B200_CUDA(cudaEventRecord(ctx->lane_done[lane], ctx->lane[lane]));
-    ctx->lane_pending[lane] = true;
-  }
+  B200_CUDA(mem_prefetch(managed, bytes, to_device ? ctx->device : -1, ctx->lane[lane]));
+  B200_CUDA(cudaEventRecord(ctx->lane_done[lane], ctx->lane[lane]));
+  ctx->lane_pending[lane] = true;
   ctx->lane_dirty[lane] = true;
   return 0;
 }
@@ -406,8 +526,8 @@ int b200_advise(b200_ctx* ctx, const void* managed, size_t bytes, int is_input) 
   static const char* mode = getenv("B200_ADVISE");
   if (mode && !strcmp(mode, "none")) return 0;
   if (!(mode && !strcmp(mode, "all")) && bytes < ((size_t)64 << 20)) return 0;
-  B200_CUDA(cudaMemAdvise(managed, bytes, cudaMemAdviseSetPreferredLocation, ctx->device));
-  if (is_input) B200_CUDA(cudaMemAdvise(managed, bytes, cudaMemAdviseSetAccessedBy, cudaCpuDeviceId));
+  B200_CUDA(mem_advise(managed, bytes, cudaMemAdviseSetPreferredLocation, ctx->device));
+  if (is_input) B200_CUDA(mem_advise(managed, bytes, cudaMemAdviseSetAccessedBy, -1));
   return 0;
 }
 
@@ -465,6 +585,12 @@ int b200_sgemm(b200_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha, 
   return gemm_simt_dispatch<float>(ctx, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
 }
 
+int b200_sgemm_prepare(b200_ctx* ctx, int m, int n, int k, int lda, int ldb) {
+  B200_REQUIRE(ctx, "b200_sgemm_prepare: null context");
+  if (m <= 0 || n <= 0 || k <= 0) return 0;
+  return sgemm_tc_prepare(ctx, m, n, k, lda, ldb);
+}
+
 static int check_gemv_args(const char* who, int trans, int m, int n, const void* A, int lda,
                            const void* x, int incx, const void* y, int incy) {
   B200_REQUIRE(trans == 0 || trans == 1, "%s: bad transpose flag", who);
@@ -495,12 +621,12 @@ int b200_sgemv(b200_ctx* ctx, int trans, int m, int n, float alpha, const float*
 
 // ------------------------------------------------ Always-mode transfer engine
 
-namespace {
+namespace b200 {
 
 // Engine-private ordering: the slab / chunk pipelines know exactly which copy each
 // kernel depends on, so they use their own events instead of the conservative
 // "every lane waits for all earlier kernels" rule of b200_h2d_async (which would
-// serialise upload j+1 behind kernel j).
+// serialise upload j+1 behind kernel j).  Shared with the multi-GPU engine (mg.cu).
 int engine_event(b200_ctx* ctx, cudaEvent_t* ev) {
   if (ctx->ev_pool_size == 0) {
     for (int i = 0; i < b200_ctx::kEvPool; i++)
@@ -525,6 +651,27 @@ int record_on(b200_ctx* ctx, cudaStream_t s, cudaEvent_t* ev) {
   return 0;
 }
 
+}  // namespace b200
+
+namespace {
+
+// Bytes spanned by a column-major rows x cols block with leading dimension ld: the last
+// column ends after `rows` elements, so a minimally sized caller buffer is never over-read.
+inline size_t extent_bytes(size_t elem, int rows, int cols, int ld) {
+  return cols > 0 && rows > 0 ? elem * ((size_t)ld * (cols - 1) + rows) : 0;
+}
+
+// Download a rows x cols block.  With ld > rows only the rows are written on the host: the
+// padding between columns belongs to the caller (and, with beta == 0, holds nothing valid on
+// the device).
+inline cudaError_t download_block(void* host, const void* dev, size_t elem, int rows, int cols, int ld,
+                                  cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return cudaSuccess;
+  if (ld == rows || cols == 1)
+    return cudaMemcpyAsync(host, dev, extent_bytes(elem, rows, cols, ld), cudaMemcpyDeviceToHost, st);
+  return cudaMemcpy2DAsync(host, elem * ld, dev, elem * ld, elem * rows, cols, cudaMemcpyDeviceToHost, st);
+}
+
 template <typename T, typename GemmFn>
 int gemm_offload(b200_ctx* ctx, int m, int n, int k, T alpha, const T* hA, T* dA, int lda,
                  const T* hB, T* dB, int ldb, T beta, T* hC, T* dC, int ldc, GemmFn gemm) {
@@ -532,14 +679,18 @@ int gemm_offload(b200_ctx* ctx, int m, int n, int k, T alpha, const T* hA, T* dA
   B200_REQUIRE(m >= 0 && n >= 0 && k >= 0, "gemm_offload: negative dimension");
   if (m == 0 || n == 0) return 0;
   const size_t s = sizeof(T);
-  const size_t bytesA = s * (size_t)lda * k, bytesB = s * (size_t)ldb * n, bytesC = s * (size_t)ldc * n;
+  const size_t bytesA = extent_bytes(s, m, k, lda), bytesB = extent_bytes(s, k, n, ldb),
+               bytesC = extent_bytes(s, m, n, ldc);
+  // B200_UPLOAD_C=1 reproduces the reference's third upload even though beta == 0 makes it dead
+  const bool upload_c = beta != T(0) || ctx->opt_upload_c;
 
   // ---- small problems: one shot, fewest API calls (latency matters, not overlap).
   // C is only uploaded when beta != 0 -- with beta == 0 BLAS never reads it, so the
   // reference's third upload (cuBLAS/gemm.hh:130-131) is dead traffic.
   // (C is written over PCIe in 64-byte pieces by the small-tile kernels: beyond ~112 KiB of
   // output the one-shot path below is faster -- M=N=128..144, K=8..9: 38-44 us vs 36-40)
-  if (bytesA + bytesB + bytesC <= ctx->opt_zerocopy_gemm_bytes && bytesC <= ((size_t)112 << 10)) {
+  if (bytesA + bytesB + bytesC <= ctx->opt_zerocopy_gemm_bytes && bytesC <= ((size_t)112 << 10) &&
+      !ctx->opt_upload_c) {
     // ---- tiny problems: zero copy.  The kernel reads A and B straight from pinned host
     // memory over PCIe and writes C back the same way: one launch + one stream sync
     // instead of two uploads, a launch, a download and a sync.
@@ -555,10 +706,16 @@ int gemm_offload(b200_ctx* ctx, int m, int n, int k, T alpha, const T* hA, T* dA
   if (bytesA + bytesB + bytesC < ((size_t)16 << 20) || k == 0) {
     if (b200_h2d_async(ctx, dA, hA, bytesA, 0)) return 1;
     if (b200_h2d_async(ctx, dB, hB, bytesB, 1)) return 1;
-    if (beta != T(0))
+    if (upload_c)
       if (b200_h2d_async(ctx, dC, hC, bytesC, 2)) return 1;
     if (gemm(ctx, 0, 0, m, n, k, alpha, dA, lda, dB, ldb, beta, dC, ldc)) return 1;
-    if (b200_d2h_async(ctx, hC, dC, bytesC, 2)) return 1;
+    if (ldc == m) {
+      if (b200_d2h_async(ctx, hC, dC, bytesC, 2)) return 1;
+    } else {
+      if (engine_begin(ctx)) return 1;
+      B200_CUDA(download_block(hC, dC, s, m, n, ldc, ctx->lane[2]));
+      ctx->lane_dirty[2] = true;
+    }
     return b200_sync(ctx);
   }
 
@@ -606,7 +763,7 @@ int gemm_offload(b200_ctx* ctx, int m, int n, int k, T alpha, const T* hA, T* dA
   int posA[kMax], posB[kMax];
   bool waitedA[kMax] = {}, waitedB[kMax] = {};
   cudaStream_t up = ctx->lane[0], down = ctx->lane[2];
-  if (beta != T(0)) {
+  if (upload_c) {
     B200_CUDA(cudaMemcpyAsync(dC, hC, bytesC, cudaMemcpyHostToDevice, up));
     if (record_on(ctx, up, &ev)) return 1;
     B200_CUDA(cudaStreamWaitEvent(ctx->compute, ev, 0));
@@ -712,8 +869,7 @@ int gemm_offload(b200_ctx* ctx, int m, int n, int k, T alpha, const T* hA, T* dA
     if (done_in_slab[j] == nk) {
       if (record_on(ctx, ctx->compute, &ev)) return 1;
       B200_CUDA(cudaStreamWaitEvent(down, ev, 0));
-      B200_CUDA(cudaMemcpyAsync(hC + (size_t)j0 * ldc, dC + (size_t)j0 * ldc, s * ((size_t)ldc * (nc - 1) + m),
-                                cudaMemcpyDeviceToHost, down));
+      B200_CUDA(download_block(hC + (size_t)j0 * ldc, dC + (size_t)j0 * ldc, s, m, nc, ldc, down));
       mark(down, "down C%d", j, 0);
     }
     i = last + 1;
@@ -741,8 +897,9 @@ int gemv_offload(b200_ctx* ctx, int m, int n, T alpha, const T* hA, T* dA, int l
   B200_REQUIRE(m >= 0 && n >= 0, "gemv_offload: negative dimension");
   if (m == 0) return 0;
   const size_t s = sizeof(T);
-  const size_t bytesA = s * (size_t)lda * n;
-  if (bytesA <= ctx->opt_zerocopy_gemv_bytes) {  // zero copy, see gemm_offload
+  const size_t bytesA = extent_bytes(s, m, n, lda);
+  const bool upload_y = beta != T(0) || ctx->opt_upload_c;
+  if (bytesA <= ctx->opt_zerocopy_gemv_bytes && !ctx->opt_upload_c) {  // zero copy, see gemm_offload
     const T* zA = (const T*)device_alias(ctx, hA);
     const T* zx = (const T*)device_alias(ctx, hx);
     T* zy = (T*)device_alias(ctx, hy);
@@ -753,9 +910,9 @@ int gemv_offload(b200_ctx* ctx, int m, int n, T alpha, const T* hA, T* dA, int l
     }
   }
   if (bytesA < ((size_t)8 << 20) || n < 2) {  // one shot
-    if (b200_h2d_async(ctx, dA, hA, n ? s * ((size_t)lda * (n - 1) + m) : 0, 0)) return 1;
+    if (b200_h2d_async(ctx, dA, hA, bytesA, 0)) return 1;
     if (b200_h2d_async(ctx, dx, hx, s * (size_t)n, 1)) return 1;
-    if (beta != T(0))
+    if (upload_y)
       if (b200_h2d_async(ctx, dy, hy, s * (size_t)m, 2)) return 1;
     if (gemv(ctx, 0, m, n, alpha, dA, lda, dx, 1, beta, dy, 1)) return 1;
     if (b200_d2h_async(ctx, hy, dy, s * (size_t)m, 2)) return 1;
@@ -766,7 +923,7 @@ int gemv_offload(b200_ctx* ctx, int m, int n, T alpha, const T* hA, T* dA, int l
   if (engine_begin(ctx)) return 1;
   cudaEvent_t ev;
   B200_CUDA(cudaMemcpyAsync(dx, hx, s * (size_t)n, cudaMemcpyHostToDevice, ctx->lane[2]));
-  if (beta != T(0)) B200_CUDA(cudaMemcpyAsync(dy, hy, s * (size_t)m, cudaMemcpyHostToDevice, ctx->lane[2]));
+  if (upload_y) B200_CUDA(cudaMemcpyAsync(dy, hy, s * (size_t)m, cudaMemcpyHostToDevice, ctx->lane[2]));
   if (record_on(ctx, ctx->lane[2], &ev)) return 1;
   B200_CUDA(cudaStreamWaitEvent(ctx->compute, ev, 0));
   const int slabs = (int)std::max<size_t>(2, std::min<size_t>(16, bytesA / ((size_t)16 << 20)));

@@ -56,7 +56,7 @@ struct b200_ctx {
   bool compute_unordered = false;  // kernels issued since compute_done was recorded
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   // event ring for the transfer engine (slab / chunk dependencies)
-  static constexpr int kEvPool = 64;
+  static constexpr int kEvPool = 256;
   cudaEvent_t ev_pool[kEvPool] = {};
   int ev_pool_size = 0, ev_next = 0;
 
@@ -83,6 +83,9 @@ struct b200_ctx {
   int opt_dgemm_min = 32;  // smallest m, n the DMMA kernels take (one 32x32 tile; below: DFMA SIMT path)
   int opt_dgemm_streamk = 1;  // 1: stream-K over the partial last wave of the TMA kernel, 0: whole tiles only
   int opt_dgemm_tma = 1;   // 1: large aligned DGEMMs use the TMA-fed kernel, 0: cp.async kernel
+  // Always mode: 1 = upload C / y even when beta == 0, as the reference does
+  // (cuBLAS/gemm.hh:130-131, cuBLAS/gemv.hh:126-127); 0 = skip the dead upload.  B200_UPLOAD_C.
+  int opt_upload_c = 0;
 
   const char* last_kernel = "none";
   unsigned long long launches = 0;
@@ -94,6 +97,16 @@ namespace b200 {
 constexpr int kMaxDevices = 64;
 
 int ensure_workspace(b200_ctx* ctx, size_t bytes);
+// Transfer-engine plumbing shared by the single-GPU (b200blas.cu) and multi-GPU (mg.cu) engines.
+int engine_event(b200_ctx* ctx, cudaEvent_t* ev);               // next event of the context's ring
+int engine_begin(b200_ctx* ctx);                                // order a call after everything before it
+int record_on(b200_ctx* ctx, cudaStream_t s, cudaEvent_t* ev);  // ring event recorded on s
+// Managed-memory calls whose signature changed in CUDA 13 (cudaMemLocation).  device < 0 = the CPU.
+cudaError_t mem_prefetch(const void* p, size_t bytes, int device, cudaStream_t s);
+cudaError_t mem_advise(const void* p, size_t bytes, cudaMemoryAdvise advice, int device);
+// Device-only block from the context's cache (no pinned twin).
+int alloc_device(b200_ctx* ctx, size_t bytes, void** dev);
+int free_device(b200_ctx* ctx, void* dev);
 // Make the compute stream wait for every copy lane that has pending uploads.
 int join_lanes_into_compute(b200_ctx* ctx);
 inline void note_launch(b200_ctx* ctx, const char* name, int n = 1) {
@@ -127,6 +140,8 @@ int dgemm_tma_dispatch(b200_ctx* ctx, int m, int n, int k, double alpha,
 int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha,
                       const float* A, int lda, const float* B, int ldb,
                       float beta, float* C, int ldc);
+
+int sgemm_tc_prepare(b200_ctx* ctx, int m, int n, int k, int lda, int ldb);
 
 int probe_peak(b200_ctx* ctx, const char* which, double* result);
 

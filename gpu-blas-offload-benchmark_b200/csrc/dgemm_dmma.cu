@@ -28,6 +28,8 @@
 
 #include <algorithm>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -335,8 +337,8 @@ int launch_dmma(b200_ctx* ctx, int m, int n, int k, double alpha, const double* 
   }
   constexpr size_t SMEM = smem_bytes<BM, BN>();
   auto kern = dgemm_dmma_kernel<ALIGNED, BM, BN, WM, WN>;
-  static bool attr_set_dev[kMaxDevices] = {};
-  bool& attr_set = attr_set_dev[ctx->device % kMaxDevices];
+  static std::atomic<bool> attr_set_dev[kMaxDevices] = {};
+  std::atomic<bool>& attr_set = attr_set_dev[ctx->device % kMaxDevices];
   if (!attr_set) {
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     attr_set = true;
@@ -346,11 +348,13 @@ int launch_dmma(b200_ctx* ctx, int m, int n, int k, double alpha, const double* 
       m, n, k, alpha, A, (long long)lda, B, (long long)ldb, beta, C, (long long)ldc, tiles_m, tiles_n,
       k_per_split, partial, ctx->counters);
   B200_CUDA(cudaGetLastError());
-  static const char* names[2][2] = {{"dgemm_dmma_%dx%dx32_cp8", "dgemm_dmma_%dx%dx32_cp8_splitk"},
-                                    {"dgemm_dmma_%dx%dx32_cp16", "dgemm_dmma_%dx%dx32_cp16_splitk"}};
-  static char name[2][64];
-  snprintf(name[splits > 1], sizeof(name[0]), names[ALIGNED][splits > 1], BM, BN);
-  note_launch(ctx, name[splits > 1]);
+  // string literals per (tile, copy width, split-K): b200_last_kernel never points into shared mutable storage
+  static_assert(BM == BN && (BM == 32 || BM == 64 || BM == 128), "name table covers the square tile configs");
+  static const char* const names[3][2][2] = {
+      {{"dgemm_dmma_32x32x32_cp8", "dgemm_dmma_32x32x32_cp8_splitk"}, {"dgemm_dmma_32x32x32_cp16", "dgemm_dmma_32x32x32_cp16_splitk"}},
+      {{"dgemm_dmma_64x64x32_cp8", "dgemm_dmma_64x64x32_cp8_splitk"}, {"dgemm_dmma_64x64x32_cp16", "dgemm_dmma_64x64x32_cp16_splitk"}},
+      {{"dgemm_dmma_128x128x32_cp8", "dgemm_dmma_128x128x32_cp8_splitk"}, {"dgemm_dmma_128x128x32_cp16", "dgemm_dmma_128x128x32_cp16_splitk"}}};
+  note_launch(ctx, names[BM == 32 ? 0 : BM == 64 ? 1 : 2][ALIGNED ? 1 : 0][splits > 1 ? 1 : 0]);
   return 0;
 }
 

@@ -39,6 +39,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "common.cuh"
 #include "ptx.cuh"
 #include "tma_host.cuh"
@@ -427,7 +429,7 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   store_tile(m0, n0);
 }
 
-bool g_attr_done_dev[kMaxDevices] = {};
+std::atomic<bool> g_attr_done_dev[kMaxDevices] = {};
 
 }  // namespace
 
@@ -486,7 +488,7 @@ int dgemm_tma_dispatch(b200_ctx* ctx, int m, int n, int k, double alpha, const d
   if (make_tensor_map_2d(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, B, k, n, (uint64_t)ldb * 8, 16, BN,
                          CU_TENSOR_MAP_SWIZZLE_128B))
     return 2;
-  bool& g_attr_done = g_attr_done_dev[ctx->device % kMaxDevices];
+  std::atomic<bool>& g_attr_done = g_attr_done_dev[ctx->device % kMaxDevices];
   if (!g_attr_done) {
     B200_CUDA(cudaFuncSetAttribute(dgemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     g_attr_done = true;

@@ -66,7 +66,12 @@ int b200_ctx_device(const b200_ctx* ctx, int* device, int* sm_count);
  *   "sgemm_streamk" = "on" | "off" (CTA-pair SGEMM kernel: stream-K over the partial last wave of tiles)
  *   "sgemm_pair" = "auto" | "on" | "off" (tcgen05 SGEMM: CTA-pair 256x256 tiles vs single-CTA 128x128)
  * Defaults come from the environment at context creation: B200_SGEMM, B200_SGEMM_PAIR,
- * B200_DGEMM_TILE, B200_DGEMM_TMA, B200_DGEMM_STREAMK. */
+ * B200_DGEMM_TILE, B200_DGEMM_TMA, B200_DGEMM_STREAMK, B200_UPLOAD_C.
+ *   "upload_c"   = "off" | "on"  (Always mode: upload C / y even when beta == 0, as the reference
+ *                  does at cuBLAS/gemm.hh:130-131 and cuBLAS/gemv.hh:126-127; default off -- BLAS
+ *                  never reads the output operand when beta == 0)
+ * b200_ctx_create also sets CUDA_MODULE_LOADING=EAGER in the process environment unless the
+ * caller has set it (so no kernel is loaded inside a timed region). */
 int b200_ctx_set_option(b200_ctx* ctx, const char* key, const char* value);
 
 /* ---- memory -------------------------------------------------------------
@@ -77,6 +82,10 @@ int b200_ctx_set_option(b200_ctx* ctx, const char* key, const char* value);
  * device blocks are cached per context and reused. */
 int b200_alloc(b200_ctx* ctx, int mode, size_t bytes, void** host, void** dev);
 int b200_free(b200_ctx* ctx, int mode, void* host, void* dev);
+/* Device-only block from the same per-context cache (cudaMalloc alone): replicas and slabs
+ * that have no host twin (multi-GPU teams, callers that keep data resident). */
+int b200_alloc_device(b200_ctx* ctx, size_t bytes, void** dev);
+int b200_free_device(b200_ctx* ctx, void* dev);
 
 /* ---- data movement (asynchronous, lane in [0, B200_NUM_LANES)) ----------
  * Replace cudaMemcpyAsync H2D / D2H on s1_..s3_ (cuBLAS/gemm.hh:100-105,
@@ -122,9 +131,10 @@ int b200_dgemv(b200_ctx* ctx, int trans, int m, int n, double alpha,
  * cuBLAS/gemv.hh:120-145): upload A, B/x and C/y from PINNED host memory,
  * compute, download C/y, and return with the result valid on the host.
  * The reference issues these back to back with no overlap.  Here large GEMMs
- * run as a K-chunk pipeline (C = sum_c A(:,Kc) B(Kc,:): chunk c+1 uploads while
- * chunk c computes; the last chunk is issued per column slab of C so downloads
- * overlap too), GEMVs stream A in column slabs, small problems go in one shot.
+ * run as a dependency-driven block pipeline (A in K-chunks, B and C in column slabs, all
+ * contiguous copies down one lane; block C(:,j) += A(:,Kc) B(Kc,j) is issued as soon as its
+ * two pieces have arrived and a slab downloads as soon as its last block is done), GEMVs
+ * stream A in column slabs, small problems go in one shot, tiny ones run zero-copy.
  * h* are host pointers, d* the device buffers from b200_alloc. */
 int b200_sgemm_offload(b200_ctx* ctx, int m, int n, int k, float alpha,
                        const float* hA, float* dA, int lda, const float* hB,
@@ -140,6 +150,108 @@ int b200_sgemv_offload(b200_ctx* ctx, int m, int n, float alpha, const float* hA
 int b200_dgemv_offload(b200_ctx* ctx, int m, int n, double alpha,
                        const double* hA, double* dA, int lda, const double* hx,
                        double* dx, double beta, double* hy, double* dy);
+
+/* Pre-sizes the scratch an SGEMM of this shape needs (the 3xTF32 operand splits), outside the
+ * caller's timed region -- what cublasCreate's workspace reservation does for cuBLAS
+ * (cuBLAS/gemm.hh:46-52).  Optional: without it the first b200_sgemm of a larger shape grows
+ * the scratch itself (one synchronising reallocation). */
+int b200_sgemm_prepare(b200_ctx* ctx, int m, int n, int k, int lda, int ldb);
+
+/* ---- multi-GPU teams -----------------------------------------
+ * ONE GEMM / GEMV partitioned over the GPUs of an NVSwitch box.  The reference backend owns a
+ * single device (cudaGetDevice in gemm_gpu::initialise, cuBLAS/gemm.hh:45-63,
+ * cuBLAS/gemv.hh:45-60); with B200_NGPUS > 1 the B200 backend classes create a team there.
+ *   GEMM: member g owns a column slab of B and C and a K-share of A; shares are pushed to
+ *         every peer's replica of A over NVLink by the copy engines, sub-chunk by sub-chunk,
+ *         and consumed chunk by chunk (C_slab += A(:,Kc) B_slab(Kc,:)) while later chunks
+ *         are still in flight.
+ *   GEMV: member g owns a compact row block of A and y; x is replicated the same way.
+ * A team is either LOCAL (one process drives every member: b200_mg_create) or one RANK per
+ * process (b200_mg_create_rank + the IPC calls below). */
+typedef struct b200_mg b200_mg;
+typedef struct b200_mg_problem b200_mg_problem;
+
+#define B200_MG_HANDLE_BYTES 64
+enum { B200_MG_GEMM = 0, B200_MG_GEMV = 1 };
+/* phases of one member's step (OR them) */
+enum {
+  B200_MG_UPLOAD = 1,    /* host -> device: my K-share of A (my share of x), my slab of B (block of A) [, C / y] */
+  B200_MG_REPLICATE = 2, /* push my share to every peer's replica and wait for theirs, chunk by chunk */
+  B200_MG_COMPUTE = 4,   /* the kernels */
+  B200_MG_DOWNLOAD = 8,  /* device -> host: my slab of C / block of y */
+  B200_MG_GATHER = 16    /* push my result into member 0's full C / y over NVLink */
+};
+
+/* Pure host arithmetic (no CUDA): contiguous split of `total` into `parts`, boundaries at
+ * multiples of `align` when every part still gets >= 2 * align; and how many members a problem
+ * is worth spreading over (small problems stay on one GPU). */
+int b200_mg_partition(long long total, int parts, int index, int align, long long* start, long long* count);
+int b200_mg_active_gemm(int world, int elem, int m, int n, int k);
+int b200_mg_active_gemv(int world, int elem, int m, int n);
+
+int b200_mg_create(b200_mg** out, int ngpus); /* local team on devices 0..ngpus-1, peer access enabled */
+int b200_mg_create_rank(b200_mg** out, int device, int rank, int world);
+int b200_mg_destroy(b200_mg* mg);
+int b200_mg_size(const b200_mg* mg);
+int b200_mg_ctx(b200_mg* mg, int member, b200_ctx** ctx); /* a local member's context (allocation, options, timers) */
+int b200_mg_sync(b200_mg* mg);                             /* everything issued through local members is complete */
+/* Rank teams: 64-byte CUDA IPC handles, carried between processes by the caller.
+ * export(dev = NULL) is this rank's flag page, import(dev = NULL) attaches a peer's; with a
+ * pointer they export / map a device buffer obtained from b200_alloc (its base address). */
+int b200_mg_export(b200_mg* mg, const void* dev, void* handle64);
+int b200_mg_import(b200_mg* mg, int member, const void* handle64, void** dev);
+int b200_mg_unmap(b200_mg* mg, void* dev);
+
+typedef struct b200_mg_gemm_args {
+  int elem;             /* 4 = float, 8 = double */
+  int active;           /* members 0..active-1 take part */
+  int m, n_slab, k;     /* my part: C_slab (m x n_slab) = alpha A (m x k) B_slab (k x n_slab) + beta C_slab */
+  double alpha, beta;
+  void* const* A_rep;   /* [active] every member's replica of A, addresses valid in this process */
+  int lda;
+  const void* hA_share; /* host: first element of MY K-share of A (NULL: already in A_rep[me]) */
+  const void* hB;       /* host: my slab of B (NULL: already on the device) */
+  void* dB;
+  int ldb;
+  void* hC;             /* host: my slab of C (destination; also the source when it is uploaded) */
+  void* dC;
+  int ldc;
+  void* C_gather;       /* my slab inside member 0's full C (NULL: none) */
+  int phases;
+} b200_mg_gemm_args;
+
+typedef struct b200_mg_gemv_args {
+  int elem, active;
+  int m_blk, n;         /* my part: y_blk (m_blk) = alpha A_blk (m_blk x n) x + beta y_blk */
+  double alpha, beta;
+  void* dA;             /* my compact row block on the device */
+  int lda;
+  const void* hA;       /* host: element (first row of my block, column 0) of a matrix with leading dimension h_lda */
+  long long h_lda;
+  void* const* x_rep;   /* [active] every member's replica of x */
+  const void* hx_share; /* host: first element of MY share of x (NULL: already in x_rep[me]) */
+  void* hy;
+  void* dy;
+  void* y_gather;       /* my block inside member 0's full y (NULL: none) */
+  int phases;
+} b200_mg_gemv_args;
+
+/* One member's step; asynchronous.  Every member of the team must issue the same sequence of
+ * steps (local teams: call it for member 0..world-1 before b200_mg_sync). */
+int b200_mg_gemm(b200_mg* mg, int member, const b200_mg_gemm_args* args);
+int b200_mg_gemv(b200_mg* mg, int member, const b200_mg_gemv_args* args);
+
+/* Whole problems on a LOCAL team = the five virtuals of the backend class
+ * (cuBLAS/gemm.hh:45-237, cuBLAS/gemv.hh:45-217).  create allocates the host-visible operands
+ * the harness fills (h0 = A, h1 = B or x, h2 = C or y; pinned, or managed in unified mode) and
+ * the per-member device buffers; k is ignored for GEMV. */
+int b200_mg_problem_create(b200_mg* mg, int kind, int elem, int mode, int m, int n, int k,
+                           void** h0, void** h1, void** h2, b200_mg_problem** out);
+int b200_mg_problem_active(const b200_mg_problem* p);
+int b200_mg_problem_preloop(b200_mg_problem* p, double beta);
+int b200_mg_problem_call(b200_mg_problem* p, double alpha, double beta);
+int b200_mg_problem_postloop(b200_mg_problem* p);
+int b200_mg_problem_destroy(b200_mg_problem* p);
 
 /* ---- introspection / measurement ----------------------------------------
  * Name of the kernel path the last compute call on this context dispatched to
