@@ -103,6 +103,8 @@ SIGNATURES = {
     "b200_mg_unmap": (_c_int, [_c_void_p, _c_void_p]),
     "b200_mg_gemm": (_c_int, [_c_void_p, _c_int, _c_void_p]),
     "b200_mg_gemv": (_c_int, [_c_void_p, _c_int, _c_void_p]),
+    "b200_mg_gemm_team": (_c_int, [_c_void_p, _c_void_p]),
+    "b200_mg_gemv_team": (_c_int, [_c_void_p, _c_void_p]),
     "b200_mg_problem_create": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _pp, _pp, _pp, _pp]),
     "b200_mg_problem_active": (_c_int, [_c_void_p]),
     "b200_mg_problem_preloop": (_c_int, [_c_void_p, _c_double]),
@@ -363,21 +365,44 @@ class Team:
         self._mapped.append(p.value)
         return p.value
 
-    # -- one member's step
-    def gemm(self, member, dtype, active, m, n_slab, k, alpha, A_rep, lda, dB, ldb, beta, dC, ldc, phases,
-             hA_share=None, hB=None, hC=None, C_gather=None):
+    # -- one member's step (rank teams) / every member's step (local teams: members=[dict, ...])
+    @staticmethod
+    def _gemm_args(dtype, active, m, n_slab, k, alpha, A_rep, lda, dB, ldb, beta, dC, ldc, phases,
+                   hA_share=None, hB=None, hC=None, C_gather=None):
         arr = (ctypes.c_void_p * len(A_rep))(*[_ptr(a) for a in A_rep])
         a = MgGemmArgs(4 if dtype == "f32" else 8, active, m, n_slab, k, alpha, beta,
                        ctypes.cast(arr, _pp), lda, _ptr(hA_share), _ptr(hB), _ptr(dB), ldb, _ptr(hC), _ptr(dC), ldc,
                        _ptr(C_gather), phases)
-        _check(self._lib.b200_mg_gemm(self._h, member, ctypes.byref(a)))
+        a._keep = arr
+        return a
 
-    def gemv(self, member, dtype, active, m_blk, n, alpha, dA, lda, x_rep, beta, dy, phases,
-             hA=None, h_lda=0, hx_share=None, hy=None, y_gather=None):
+    @staticmethod
+    def _gemv_args(dtype, active, m_blk, n, alpha, dA, lda, x_rep, beta, dy, phases,
+                   hA=None, h_lda=0, hx_share=None, hy=None, y_gather=None):
         arr = (ctypes.c_void_p * len(x_rep))(*[_ptr(a) for a in x_rep])
         a = MgGemvArgs(4 if dtype == "f32" else 8, active, m_blk, n, alpha, beta, _ptr(dA), lda, _ptr(hA), h_lda,
                        ctypes.cast(arr, _pp), _ptr(hx_share), _ptr(hy), _ptr(dy), _ptr(y_gather), phases)
+        a._keep = arr
+        return a
+
+    def gemm(self, member, *args, **kw):
+        a = self._gemm_args(*args, **kw)
+        _check(self._lib.b200_mg_gemm(self._h, member, ctypes.byref(a)))
+
+    def gemv(self, member, *args, **kw):
+        a = self._gemv_args(*args, **kw)
         _check(self._lib.b200_mg_gemv(self._h, member, ctypes.byref(a)))
+
+    def gemm_team(self, members):
+        """members[g] = dict of the arguments of gemm() for member g (local teams)."""
+        items = [self._gemm_args(**kw) for kw in members]
+        arr = (MgGemmArgs * len(items))(*items)
+        _check(self._lib.b200_mg_gemm_team(self._h, arr))
+
+    def gemv_team(self, members):
+        items = [self._gemv_args(**kw) for kw in members]
+        arr = (MgGemvArgs * len(items))(*items)
+        _check(self._lib.b200_mg_gemv_team(self._h, arr))
 
     # -- whole problems (local teams): the five virtuals of the backend class
     def problem(self, kind, dtype, mode, m, n, k=0):

@@ -34,6 +34,11 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -65,6 +70,20 @@ struct MgMember {
   uint32_t ops = 0;             // team operations issued so far = the epoch of the last one
 };
 
+// One host thread per member of a LOCAL team.  A member's step is issued asynchronously, but an
+// issue can still block on its own device (a lazily loaded module, scratch growth, a full launch
+// queue) while that device waits for a flag only a peer's step will raise -- so the members of a
+// team must never be issued one after the other from a single thread.
+struct MgWorker {
+  std::thread th;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::function<int()> job;
+  bool has_job = false, done = false, quit = false;
+  int rc = 0;
+  char err[512] = {};
+};
+
 }  // namespace
 
 struct b200_mg {
@@ -75,6 +94,7 @@ struct b200_mg {
   wait_value32_fn wait_value32 = nullptr;
   int opt_sub = 0, opt_pieces = 0;  // tuning overrides (B200_MG_SUB, B200_MG_PIECES)
   size_t opt_chunk_bytes = (size_t)256 << 20;
+  MgWorker* workers = nullptr;  // local teams with more than one member
 };
 
 struct b200_mg_problem {
@@ -548,6 +568,73 @@ int gemv_step(b200_mg* mg, int g, const b200_mg_gemv_args& a) {
   return 0;
 }
 
+void worker_main(MgWorker* w) {
+  std::unique_lock<std::mutex> lk(w->mu);
+  for (;;) {
+    w->cv.wait(lk, [&] { return w->has_job || w->quit; });
+    if (w->quit) return;
+    w->rc = w->job();
+    if (w->rc) snprintf(w->err, sizeof(w->err), "%s", b200_last_error());
+    w->has_job = false;
+    w->done = true;
+    w->cv.notify_all();
+  }
+}
+
+void start_workers(b200_mg* mg) {
+  if (mg->self >= 0 || mg->world < 2) return;
+  mg->workers = new MgWorker[mg->world];
+  for (int g = 0; g < mg->world; g++) mg->workers[g].th = std::thread(worker_main, &mg->workers[g]);
+}
+
+void stop_workers(b200_mg* mg) {
+  if (!mg->workers) return;
+  for (int g = 0; g < mg->world; g++) {
+    {
+      std::lock_guard<std::mutex> lk(mg->workers[g].mu);
+      mg->workers[g].quit = true;
+    }
+    mg->workers[g].cv.notify_all();
+    if (mg->workers[g].th.joinable()) mg->workers[g].th.join();
+  }
+  delete[] mg->workers;
+  mg->workers = nullptr;
+}
+
+// fn(g) for every member, each from its own thread; returns the first failure
+int run_members(b200_mg* mg, int active, const std::function<int(int)>& fn) {
+  if (!mg->workers || active <= 1) {  // nobody waits for a peer: plain calls, no thread hand-off
+    for (int g = 0; g < mg->world; g++)
+      if (mg->mem[g].ctx)
+        if (int rc = fn(g)) return rc;
+    return 0;
+  }
+  for (int g = 0; g < mg->world; g++) {
+    MgWorker& w = mg->workers[g];
+    {
+      std::lock_guard<std::mutex> lk(w.mu);
+      w.job = [&fn, g] { return fn(g); };
+      w.done = false;
+      w.has_job = true;
+    }
+    w.cv.notify_all();
+  }
+  int rc = 0;
+  for (int g = 0; g < mg->world; g++) {
+    MgWorker& w = mg->workers[g];
+    std::unique_lock<std::mutex> lk(w.mu);
+    w.cv.wait(lk, [&] { return w.done; });
+    if (w.rc && !rc) {
+      rc = w.rc;
+      set_error("%s", w.err);
+    }
+  }
+  int dev = 0;
+  if (mg->mem[0].ctx) dev = mg->mem[0].ctx->device;
+  cudaSetDevice(dev);
+  return rc;
+}
+
 int sync_member(MgMember& me) {
   if (!me.ctx) return 0;
   B200_CUDA(cudaStreamSynchronize(me.push));
@@ -629,6 +716,7 @@ int b200_mg_create(b200_mg** out, int ngpus) {
     }
   }
   cudaSetDevice(restore);
+  start_workers(mg);
   *out = mg;
   return 0;
 }
@@ -648,6 +736,7 @@ int b200_mg_create_rank(b200_mg** out, int device, int rank, int world) {
 
 int b200_mg_destroy(b200_mg* mg) {
   if (!mg) return 0;
+  stop_workers(mg);
   for (int g = 0; g < mg->world; g++) {
     MgMember& me = mg->mem[g];
     if (me.ctx) {
@@ -731,6 +820,16 @@ int b200_mg_gemv(b200_mg* mg, int member, const b200_mg_gemv_args* args) {
   return args->elem == 8 ? gemv_step<double>(mg, member, *args) : gemv_step<float>(mg, member, *args);
 }
 
+int b200_mg_gemm_team(b200_mg* mg, const b200_mg_gemm_args* args) {
+  B200_REQUIRE(mg && args, "b200_mg_gemm_team: null argument");
+  return run_members(mg, args[0].active, [mg, args](int g) { return b200_mg_gemm(mg, g, &args[g]); });
+}
+
+int b200_mg_gemv_team(b200_mg* mg, const b200_mg_gemv_args* args) {
+  B200_REQUIRE(mg && args, "b200_mg_gemv_team: null argument");
+  return run_members(mg, args[0].active, [mg, args](int g) { return b200_mg_gemv(mg, g, &args[g]); });
+}
+
 // ------------------------------------------------------------------ whole problems (local teams)
 //
 // The five virtuals of the reference backend class (initialise / preLoopRequirements / callGemm
@@ -757,6 +856,12 @@ int b200_mg_problem_create(b200_mg* mg, int kind, int elem, int mode, int m, int
     p->active = b200_mg_active_gemv(mg->world, elem, m, n);
     p->bytes[0] = s * (size_t)m * n; p->bytes[1] = s * (size_t)n; p->bytes[2] = s * (size_t)m;
   }
+  // Unified mode stays on ONE GPU unless B200_MG_UNIFIED=spread: managed pages migrate 2 MiB at a
+  // time under the UVM driver, and operands shared (A, x) or strided (row blocks) across GPUs
+  // ping-pong -- measured with the harness, 2 GPUs: DGEMM 4096^3 26.2 -> 2.7 TFLOP/s, DGEMV 8192^2
+  // 106 -> 1.2 GFLOP/s (profiles/r2_multigpu.md).
+  static const bool spread_unified = getenv("B200_MG_UNIFIED") && !strcmp(getenv("B200_MG_UNIFIED"), "spread");
+  if (mode == B200_OFFLOAD_UNIFIED && !spread_unified) p->active = 1;
   for (int i = 0; i < 3; i++)
     if (b200_alloc(c0, mode, p->bytes[i], &p->h[i], &p->d0[i])) { b200_mg_problem_destroy(p); return 1; }
   const int W = p->active;
@@ -822,9 +927,10 @@ static int problem_step(b200_mg_problem* p, int phases, double alpha, double bet
   b200_mg* mg = p->mg;
   const int W = p->active;
   const size_t s = (size_t)p->elem;
-  for (int g = 0; g < mg->world; g++) {
-    if (p->kind == B200_MG_GEMM) {
-      b200_mg_gemm_args a = {};
+  if (p->kind == B200_MG_GEMM) {
+    b200_mg_gemm_args args[kMaxTeam] = {};
+    for (int g = 0; g < mg->world; g++) {
+      b200_mg_gemm_args& a = args[g];
       a.elem = p->elem; a.active = W; a.m = p->m; a.n_slab = g < W ? (int)p->count[g] : 0; a.k = p->k;
       a.alpha = alpha; a.beta = beta;
       a.A_rep = p->rep; a.lda = std::max(1, p->m); a.ldb = std::max(1, p->k); a.ldc = std::max(1, p->m);
@@ -835,27 +941,49 @@ static int problem_step(b200_mg_problem* p, int phases, double alpha, double bet
         a.dB = p->slab[g]; a.dC = p->out[g];
       }
       a.phases = phases;
-      if (b200_mg_gemm(mg, g, &a)) return 1;
-    } else {
-      b200_mg_gemv_args a = {};
-      a.elem = p->elem; a.active = W; a.m_blk = g < W ? (int)p->count[g] : 0; a.n = p->n;
-      a.alpha = alpha; a.beta = beta;
-      a.x_rep = p->rep;
-      if (g < W) {
-        a.dA = p->slab[g]; a.lda = std::max<long long>(1, W == 1 ? p->m : p->count[g]);
-        a.hA = (char*)p->h[0] + s * (size_t)p->start[g]; a.h_lda = std::max(1, p->m);
-        a.hx_share = (char*)p->h[1] + s * (size_t)p->share0[g];
-        a.hy = (char*)p->h[2] + s * (size_t)p->start[g]; a.dy = p->out[g];
-      }
-      a.phases = phases;
-      if (b200_mg_gemv(mg, g, &a)) return 1;
     }
+    return b200_mg_gemm_team(mg, args);
   }
-  return 0;
+  b200_mg_gemv_args args[kMaxTeam] = {};
+  for (int g = 0; g < mg->world; g++) {
+    b200_mg_gemv_args& a = args[g];
+    a.elem = p->elem; a.active = W; a.m_blk = g < W ? (int)p->count[g] : 0; a.n = p->n;
+    a.alpha = alpha; a.beta = beta;
+    a.x_rep = p->rep;
+    if (g < W) {
+      a.dA = p->slab[g]; a.lda = (int)std::max<long long>(1, W == 1 ? p->m : p->count[g]);
+      a.hA = (char*)p->h[0] + s * (size_t)p->start[g]; a.h_lda = std::max(1, p->m);
+      a.hx_share = (char*)p->h[1] + s * (size_t)p->share0[g];
+      a.hy = (char*)p->h[2] + s * (size_t)p->start[g]; a.dy = p->out[g];
+    }
+    a.phases = phases;
+  }
+  return b200_mg_gemv_team(mg, args);
 }
+
+// B200_MG_TRACE=1: host wall time of each problem-level call, with a sync after it (diagnostic)
+static bool mg_trace() {
+  static const bool t = getenv("B200_MG_TRACE") != nullptr;
+  return t;
+}
+struct TraceScope {
+  b200_mg_problem* p;
+  const char* what;
+  std::chrono::steady_clock::time_point t0;
+  TraceScope(b200_mg_problem* p_, const char* w) : p(p_), what(w), t0(std::chrono::steady_clock::now()) {}
+  ~TraceScope() {
+    if (!mg_trace()) return;
+    const double issue = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    b200_mg_sync(p->mg);
+    const double done = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    fprintf(stderr, "[b200 mg] %-8s kind=%d elem=%d mode=%d m=%d n=%d k=%d active=%d: issued %.3f ms, complete %.3f ms\n", what,
+            p->kind, p->elem, p->mode, p->m, p->n, p->k, p->active, issue, done);
+  }
+};
 
 int b200_mg_problem_preloop(b200_mg_problem* p, double beta) {
   B200_REQUIRE(p, "b200_mg_problem_preloop: null problem");
+  TraceScope ts(p, "preloop");
   b200_mg* mg = p->mg;
   if (p->mode == B200_OFFLOAD_ONCE) return problem_step(p, B200_MG_UPLOAD | B200_MG_REPLICATE, 1.0, beta);
   if (p->mode == B200_OFFLOAD_UNIFIED) {
@@ -885,6 +1013,7 @@ int b200_mg_problem_preloop(b200_mg_problem* p, double beta) {
 
 int b200_mg_problem_call(b200_mg_problem* p, double alpha, double beta) {
   B200_REQUIRE(p, "b200_mg_problem_call: null problem");
+  TraceScope ts(p, "call");
   b200_mg* mg = p->mg;
   if (p->mode == B200_OFFLOAD_ALWAYS) {
     if (p->active == 1) {  // small problems: the single-GPU transfer engine (zero copy / one shot / block pipeline)
@@ -923,6 +1052,7 @@ int b200_mg_problem_call(b200_mg_problem* p, double alpha, double beta) {
 
 int b200_mg_problem_postloop(b200_mg_problem* p) {
   B200_REQUIRE(p, "b200_mg_problem_postloop: null problem");
+  TraceScope ts(p, "postloop");
   b200_mg* mg = p->mg;
   if (p->mode == B200_OFFLOAD_ONCE) {
     if (problem_step(p, B200_MG_DOWNLOAD, 1.0, 0.0)) return 1;

