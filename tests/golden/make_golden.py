@@ -10,6 +10,11 @@ and records
   reference_checksums.json  -- the harness checksum (kernels/gemm.hh:61-65,
                                kernels/gemv.hh:61-65) per shape, FP64 and FP32
   reference_outputs.npz     -- the full C / y the reference produced per shape
+  reference_samples.npz     -- for shapes whose output is too large to commit (the sizes the
+                               TMA-DMMA, tcgen05 single-CTA and CTA-pair kernels take, and the
+                               reference's rectangular problem types at D = 8192): 4096 output
+                               elements at fixed pseudo-random positions (+ the 4 corners), FP64
+                               and FP32, plus their positions
 
 The inputs are not stored: they are the reference's deterministic generator
 (srand(19123005), include/kernels/gemm.hh:69-87), which oracle/blob_oracle.c
@@ -33,6 +38,20 @@ GEMM_SHAPES = [
 ]
 # checksum-only (outputs too large to commit): SURVEY.md 9.3 table
 GEMM_CHECKSUM_ONLY = [(1024, 1024, 1024), (2048, 2048, 32), (4096, 64, 4096)]
+# sampled-element fixtures: square sizes of the flagship kernels + the cfg3 problem types
+# (include/doGemm.hh:91-285) at D = 8192
+GEMM_SAMPLED = [(1024, 1024, 1024), (2048, 2048, 512), (2048, 2048, 2048), (4096, 4096, 4096),
+                (512, 512, 8192), (8192, 512, 512), (512, 8192, 512), (8192, 8192, 512), (8192, 8192, 32),
+                (32, 32, 8192), (8192, 32, 32), (32, 8192, 32)]
+SAMPLES = 4096
+
+
+def sample_positions(m, n):
+    rng = np.random.default_rng(m * 1000003 + n)
+    pos = rng.integers(0, m * n, SAMPLES - 4)
+    return np.concatenate([pos, [0, m - 1, m * (n - 1), m * n - 1]]).astype(np.int64)
+
+
 GEMV_SHAPES = [
     (1, 1), (2, 2), (3, 7), (32, 32), (128, 128), (1024, 1024), (4096, 4096),
     (32, 8192), (8192, 32), (2048, 128), (127, 129), (1001, 77), (33, 2050),
@@ -70,6 +89,20 @@ def main():
         d = run_gemv(lib.blobref_dgemv, np.float64, m, n)
         s = run_gemv(lib.blobref_sgemv, np.float32, m, n)
         sums["gemv"].append({"m": m, "n": n, "dgemv": d, "sgemv": s})
+
+    samples = {}
+    for (m, n, k) in GEMM_SAMPLED:
+        pos = sample_positions(m, n)
+        for fn, dtype, tag in ((lib.blobref_dgemm, np.float64, "d"), (lib.blobref_sgemm, np.float32, "s")):
+            c = np.zeros(m * n, dtype=dtype)
+            cs = ctypes.c_double()
+            fn(m, n, k, 1, c.ctypes.data_as(ctypes.c_void_p), ctypes.byref(cs), None)
+            samples[f"{tag}gemm_{m}_{n}_{k}"] = c[pos]
+            if not any((r["m"], r["n"], r["k"]) == (m, n, k) for r in sums["gemm"]):
+                sums["gemm"].append({"m": m, "n": n, "k": k})
+            [r for r in sums["gemm"] if (r["m"], r["n"], r["k"]) == (m, n, k)][0][f"{tag}gemm"] = cs.value
+        samples[f"pos_{m}_{n}"] = pos
+    np.savez_compressed(os.path.join(HERE, "reference_samples.npz"), **samples)
 
     with open(os.path.join(HERE, "reference_checksums.json"), "w") as f:
         json.dump(sums, f, indent=1)

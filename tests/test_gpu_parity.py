@@ -152,6 +152,37 @@ def test_large_golden_checksums(blob, ctx, oracle, row):
         assert abs(cs - row[key]) <= TOL[dt] * abs(row[key]), (dt, kern, cs, row[key])
 
 
+SAMPLES = np.load(os.path.join(HERE, "golden", "reference_samples.npz"))
+# which kernel family must have produced each sampled shape (so the fixture really meets the
+# flagship kernels, not the small-tile fallbacks)
+SAMPLED_KERNELS = {
+    ("f64", (2048, 2048, 2048)): "dgemm_dmma_tma", ("f64", (4096, 4096, 4096)): "dgemm_dmma_tma",
+    ("f64", (8192, 8192, 512)): "dgemm_dmma_tma", ("f64", (512, 512, 8192)): "dgemm_dmma_tma",
+    ("f32", (2048, 2048, 2048)): "sgemm_3xtf32_tcgen05", ("f32", (4096, 4096, 4096)): "sgemm_3xtf32_tcgen05_pair",
+    ("f32", (8192, 8192, 512)): "sgemm_3xtf32_tcgen05_pair", ("f32", (1024, 1024, 1024)): "sgemm_3xtf32_tcgen05",
+    ("f32", (512, 512, 8192)): "sgemm_3xtf32_tcgen05",
+}
+
+
+@pytest.mark.parametrize("dt", ["f64", "f32"])
+@pytest.mark.parametrize("shape", sorted({tuple(int(x) for x in k.split("_")[1:]) for k in SAMPLES.files if k[1:5] == "gemm"}),
+                         ids=lambda s: "x".join(map(str, s)))
+def test_sampled_reference_outputs(blob, ctx, oracle, shape, dt):
+    """4096 output elements per shape as the REFERENCE's own OpenBLAS classes produced them
+    (tests/golden/make_golden.py), at the sizes the TMA-DMMA, tcgen05 and CTA-pair kernels take
+    and at the reference's rectangular problem types for D = 8192 (include/doGemm.hh:91-285)."""
+    m, n, k = shape
+    A, B, _ = oracle.init_gemm(dt, m, n, k)
+    got, kern = run_gemm(blob, ctx, dt, "once", m, n, k, A, B)
+    pos = SAMPLES[f"pos_{m}_{n}"]
+    want = SAMPLES[f"{'d' if dt == 'f64' else 's'}gemm_{m}_{n}_{k}"]
+    err = max_rel_err(got[pos], want)
+    assert err <= TOL[dt], (dt, shape, kern, err)
+    must = SAMPLED_KERNELS.get((dt, shape))
+    if must:
+        assert kern.startswith(must), (dt, shape, kern)
+
+
 # ------------------------------------------------------- oracle, many shapes ---
 
 GEMM_SHAPES = [
