@@ -81,7 +81,7 @@ def build_library(force=False, verbose=False):
         objs.append(obj)
     if rebuilt or not os.path.exists(LIB):
         _run([NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
-                                                     "-cudart", "static"])
+                                                     "-cudart", "static", "-ldl"])
     if log:
         with open(os.path.join(LIBDIR, "ptxas.log"), "w") as f:
             f.write("\n".join(log))

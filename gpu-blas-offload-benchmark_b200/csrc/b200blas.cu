@@ -17,11 +17,30 @@
 
 #include <algorithm>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "common.cuh"
 
 namespace b200 {
 
 static thread_local char g_error[512] = "no error";
+
+bool profile_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("B200_PROFILE");
+    return e != nullptr && strcmp(e, "0") != 0;
+  }();
+  return on;
+}
+void profile_push(const char* fmt, ...) {
+  char buf[160];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  nvtxRangePushA(buf);
+}
+void profile_pop() { nvtxRangePop(); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -562,6 +581,7 @@ static int check_gemm_args(const char* who, int ta, int tb, int m, int n, int k,
 int b200_dgemm(b200_ctx* ctx, int ta, int tb, int m, int n, int k, double alpha, const double* A,
                int lda, const double* B, int ldb, double beta, double* C, int ldc) {
   B200_REQUIRE(ctx, "b200_dgemm: null context");
+  ProfileRange pr("b200_dgemm %dx%dx%d", m, n, k);
   if (int r = check_gemm_args("b200_dgemm", ta, tb, m, n, k, A, lda, B, ldb, C, ldc)) return r;
   if (m == 0 || n == 0) return 0;
   if (join_lanes_into_compute(ctx)) return 1;
@@ -575,6 +595,7 @@ int b200_dgemm(b200_ctx* ctx, int ta, int tb, int m, int n, int k, double alpha,
 int b200_sgemm(b200_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha, const float* A,
                int lda, const float* B, int ldb, float beta, float* C, int ldc) {
   B200_REQUIRE(ctx, "b200_sgemm: null context");
+  ProfileRange pr("b200_sgemm %dx%dx%d", m, n, k);
   if (int r = check_gemm_args("b200_sgemm", ta, tb, m, n, k, A, lda, B, ldb, C, ldc)) return r;
   if (m == 0 || n == 0) return 0;
   if (join_lanes_into_compute(ctx)) return 1;
@@ -604,6 +625,7 @@ static int check_gemv_args(const char* who, int trans, int m, int n, const void*
 int b200_dgemv(b200_ctx* ctx, int trans, int m, int n, double alpha, const double* A, int lda,
                const double* x, int incx, double beta, double* y, int incy) {
   B200_REQUIRE(ctx, "b200_dgemv: null context");
+  ProfileRange pr("b200_dgemv %dx%d", m, n);
   if (int r = check_gemv_args("b200_dgemv", trans, m, n, A, lda, x, incx, y, incy)) return r;
   if (join_lanes_into_compute(ctx)) return 1;
   return gemv_dispatch<double>(ctx, trans, m, n, alpha, A, lda, x, incx, beta, y, incy);
@@ -612,6 +634,7 @@ int b200_dgemv(b200_ctx* ctx, int trans, int m, int n, double alpha, const doubl
 int b200_sgemv(b200_ctx* ctx, int trans, int m, int n, float alpha, const float* A, int lda,
                const float* x, int incx, float beta, float* y, int incy) {
   B200_REQUIRE(ctx, "b200_sgemv: null context");
+  ProfileRange pr("b200_sgemv %dx%d", m, n);
   if (int r = check_gemv_args("b200_sgemv", trans, m, n, A, lda, x, incx, y, incy)) return r;
   if (join_lanes_into_compute(ctx)) return 1;
   return gemv_dispatch<float>(ctx, trans, m, n, alpha, A, lda, x, incx, beta, y, incy);
@@ -676,6 +699,7 @@ template <typename T, typename GemmFn>
 int gemm_offload(b200_ctx* ctx, int m, int n, int k, T alpha, const T* hA, T* dA, int lda,
                  const T* hB, T* dB, int ldb, T beta, T* hC, T* dC, int ldc, GemmFn gemm) {
   B200_REQUIRE(ctx && hA && dA && hB && dB && hC && dC, "gemm_offload: null argument");
+  ProfileRange pr("b200_%cgemm_offload %dx%dx%d", sizeof(T) == 8 ? 'd' : 's', m, n, k);
   B200_REQUIRE(m >= 0 && n >= 0 && k >= 0, "gemm_offload: negative dimension");
   if (m == 0 || n == 0) return 0;
   const size_t s = sizeof(T);
@@ -894,6 +918,7 @@ template <typename T, typename GemvFn>
 int gemv_offload(b200_ctx* ctx, int m, int n, T alpha, const T* hA, T* dA, int lda, const T* hx,
                  T* dx, T beta, T* hy, T* dy, GemvFn gemv) {
   B200_REQUIRE(ctx && hA && dA && hx && dx && hy && dy, "gemv_offload: null argument");
+  ProfileRange pr("b200_%cgemv_offload %dx%d", sizeof(T) == 8 ? 'd' : 's', m, n);
   B200_REQUIRE(m >= 0 && n >= 0, "gemv_offload: negative dimension");
   if (m == 0) return 0;
   const size_t s = sizeof(T);

@@ -145,6 +145,25 @@ int sgemm_tc_prepare(b200_ctx* ctx, int m, int n, int k, int lda, int ldb);
 
 int probe_peak(b200_ctx* ctx, const char* which, double* result);
 
+// ---- profiling hooks -----------------------------------
+// B200_PROFILE=1 wraps every ABI call that issues device work in an NVTX range (header-only
+// NVTX3: the tool's library is loaded only when a profiler is attached), so an nsys / ncu
+// timeline shows "b200_dgemm 8192x8192x8192", "b200_dgemm_offload ...", "mg gemm step ..."
+// next to the kernels.  Off by default: one getenv at start-up, one branch per call.
+bool profile_enabled();
+void profile_push(const char* fmt, ...);
+void profile_pop();
+struct ProfileRange {
+  bool on;
+  template <typename... Args>
+  explicit ProfileRange(const char* fmt, Args... args) : on(profile_enabled()) {
+    if (on) profile_push(fmt, args...);
+  }
+  ~ProfileRange() {
+    if (on) profile_pop();
+  }
+};
+
 // ---- device helpers --------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
