@@ -264,7 +264,7 @@ int b200_ctx_create(b200_ctx** out, int device) {
   }
   if (device < 0) B200_CUDA(cudaGetDevice(&device));
   B200_REQUIRE(device < count, "b200_ctx_create: device %d out of range (%d)", device, count);
-  B200_CUDA(cudaSetDevice(device));
+  DeviceScope ds(device);
   cudaDeviceProp prop;
   B200_CUDA(cudaGetDeviceProperties(&prop, device));
   B200_REQUIRE(prop.major == 10, "b200_ctx_create: device %d is sm_%d%d; this build is sm_100a only",
@@ -290,6 +290,7 @@ int b200_ctx_create(b200_ctx** out, int device) {
   if (const char* e = getenv("B200_SGEMM")) ctx->opt_sgemm = !strcmp(e, "tc") ? 1 : !strcmp(e, "ffma") ? 2 : 0;
   if (const char* e = getenv("B200_SGEMM_STREAMK")) ctx->opt_sgemm_streamk = strcmp(e, "off") != 0 && strcmp(e, "0") != 0;
   if (const char* e = getenv("B200_SGEMM_PAIR")) ctx->opt_sgemm_pair = !strcmp(e, "on") ? 1 : !strcmp(e, "off") ? 2 : 0;
+  if (const char* e = getenv("B200_SGEMM_FUSED")) ctx->opt_sgemm_fused = !strcmp(e, "on") ? 1 : !strcmp(e, "off") ? 2 : 0;
   if (const char* e = getenv("B200_ZEROCOPY_GEMM_BYTES")) ctx->opt_zerocopy_gemm_bytes = (size_t)atoll(e);
   if (const char* e = getenv("B200_ZEROCOPY_GEMV_BYTES")) ctx->opt_zerocopy_gemv_bytes = (size_t)atoll(e);
   if (const char* e = getenv("B200_DGEMM_MIN")) ctx->opt_dgemm_min = atoi(e);
@@ -311,7 +312,7 @@ int b200_ctx_create(b200_ctx** out, int device) {
 
 int b200_ctx_destroy(b200_ctx* ctx) {
   if (!ctx) return 0;
-  cudaSetDevice(ctx->device);
+  DeviceScope ds(ctx->device);
   if (ctx->own_compute) cudaStreamSynchronize(ctx->own_compute);
   for (int l = 0; l < B200_NUM_LANES; l++)
     if (ctx->lane[l]) cudaStreamSynchronize(ctx->lane[l]);
@@ -361,6 +362,13 @@ int b200_ctx_set_option(b200_ctx* ctx, const char* key, const char* value) {
     else B200_REQUIRE(false, "b200_ctx_set_option: sgemm_pair must be auto|on|off, got '%s'", value);
     return 0;
   }
+  if (!strcmp(key, "sgemm_fused")) {
+    if (!strcmp(value, "auto")) ctx->opt_sgemm_fused = 0;
+    else if (!strcmp(value, "on")) ctx->opt_sgemm_fused = 1;
+    else if (!strcmp(value, "off")) ctx->opt_sgemm_fused = 2;
+    else B200_REQUIRE(false, "b200_ctx_set_option: sgemm_fused must be auto|on|off, got '%s'", value);
+    return 0;
+  }
   if (!strcmp(key, "dgemm_tile")) {
     if (!strcmp(value, "auto")) ctx->opt_dgemm_tile = 0;
     else if (!strcmp(value, "32")) ctx->opt_dgemm_tile = 32;
@@ -400,6 +408,7 @@ int b200_ctx_device(const b200_ctx* ctx, int* device, int* sm_count) {
 
 int b200_alloc(b200_ctx* ctx, int mode, size_t bytes, void** host, void** dev) {
   B200_REQUIRE(ctx && host && dev, "b200_alloc: null argument");
+  DeviceScope ds(ctx->device);
   *host = *dev = nullptr;
   if (bytes == 0) bytes = 1;
   if (mode == B200_OFFLOAD_UNIFIED) {
@@ -453,6 +462,7 @@ int b200_alloc(b200_ctx* ctx, int mode, size_t bytes, void** host, void** dev) {
 
 int b200_free(b200_ctx* ctx, int mode, void* host, void* dev) {
   B200_REQUIRE(ctx, "b200_free: null context");
+  DeviceScope ds(ctx->device);
   if (mode == B200_OFFLOAD_UNIFIED) {
     if (!host) return 0;
     if (ctx->compute_dirty || ctx->lane_dirty[0] || ctx->lane_dirty[1] || ctx->lane_dirty[2])
@@ -487,13 +497,14 @@ int b200_free(b200_ctx* ctx, int mode, void* host, void* dev) {
 
 int b200_alloc_device(b200_ctx* ctx, size_t bytes, void** dev) {
   B200_REQUIRE(ctx && dev, "b200_alloc_device: null argument");
+  DeviceScope ds(ctx->device);
   *dev = nullptr;
-  B200_CUDA(cudaSetDevice(ctx->device));
   return alloc_device(ctx, bytes, dev);
 }
 
 int b200_free_device(b200_ctx* ctx, void* dev) {
   B200_REQUIRE(ctx, "b200_free_device: null context");
+  DeviceScope ds(ctx->device);
   if (ctx->compute_dirty || ctx->lane_dirty[0] || ctx->lane_dirty[1] || ctx->lane_dirty[2])
     if (b200_sync(ctx)) return 1;
   return free_device(ctx, dev);
@@ -501,6 +512,7 @@ int b200_free_device(b200_ctx* ctx, void* dev) {
 
 int b200_h2d_async(b200_ctx* ctx, void* dev, const void* host, size_t bytes, int lane) {
   B200_REQUIRE(ctx && lane >= 0 && lane < B200_NUM_LANES, "b200_h2d_async: bad lane %d", lane);
+  DeviceScope ds(ctx->device);
   if (bytes == 0) return 0;
   if (lanes_wait_for_compute(ctx)) return 1;
   B200_CUDA(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx->lane[lane]));
@@ -512,6 +524,7 @@ int b200_h2d_async(b200_ctx* ctx, void* dev, const void* host, size_t bytes, int
 
 int b200_d2h_async(b200_ctx* ctx, void* host, const void* dev, size_t bytes, int lane) {
   B200_REQUIRE(ctx && lane >= 0 && lane < B200_NUM_LANES, "b200_d2h_async: bad lane %d", lane);
+  DeviceScope ds(ctx->device);
   if (bytes == 0) return 0;
   if (lanes_wait_for_compute(ctx)) return 1;
   B200_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->lane[lane]));
@@ -525,6 +538,7 @@ int b200_d2h_async(b200_ctx* ctx, void* host, const void* dev, size_t bytes, int
 
 int b200_prefetch_async(b200_ctx* ctx, const void* managed, size_t bytes, int to_device, int lane) {
   B200_REQUIRE(ctx && lane >= 0 && lane < B200_NUM_LANES, "b200_prefetch_async: bad lane %d", lane);
+  DeviceScope ds(ctx->device);
   if (bytes == 0) return 0;
   if (lanes_wait_for_compute(ctx)) return 1;
   B200_CUDA(mem_prefetch(managed, bytes, to_device ? ctx->device : -1, ctx->lane[lane]));
@@ -536,6 +550,7 @@ int b200_prefetch_async(b200_ctx* ctx, const void* managed, size_t bytes, int to
 
 int b200_advise(b200_ctx* ctx, const void* managed, size_t bytes, int is_input) {
   B200_REQUIRE(ctx && managed, "b200_advise: null argument");
+  DeviceScope ds(ctx->device);
   if (bytes == 0) return 0;
   // Measured with the unmodified harness (scripts/unified_ab.sh, profiles/r1_unified_ab.txt):
   // on operands of a few MB the advice costs more than it saves (median 96 vs 63 us per
@@ -552,6 +567,7 @@ int b200_advise(b200_ctx* ctx, const void* managed, size_t bytes, int is_input) 
 
 int b200_sync(b200_ctx* ctx) {
   B200_REQUIRE(ctx, "b200_sync: null context");
+  DeviceScope ds(ctx->device);
   B200_CUDA(cudaStreamSynchronize(ctx->compute));
   for (int l = 0; l < B200_NUM_LANES; l++) {
     if (ctx->lane_dirty[l]) B200_CUDA(cudaStreamSynchronize(ctx->lane[l]));
@@ -581,6 +597,7 @@ static int check_gemm_args(const char* who, int ta, int tb, int m, int n, int k,
 int b200_dgemm(b200_ctx* ctx, int ta, int tb, int m, int n, int k, double alpha, const double* A,
                int lda, const double* B, int ldb, double beta, double* C, int ldc) {
   B200_REQUIRE(ctx, "b200_dgemm: null context");
+  DeviceScope ds(ctx->device);
   ProfileRange pr("b200_dgemm %dx%dx%d", m, n, k);
   if (int r = check_gemm_args("b200_dgemm", ta, tb, m, n, k, A, lda, B, ldb, C, ldc)) return r;
   if (m == 0 || n == 0) return 0;
@@ -595,6 +612,7 @@ int b200_dgemm(b200_ctx* ctx, int ta, int tb, int m, int n, int k, double alpha,
 int b200_sgemm(b200_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha, const float* A,
                int lda, const float* B, int ldb, float beta, float* C, int ldc) {
   B200_REQUIRE(ctx, "b200_sgemm: null context");
+  DeviceScope ds(ctx->device);
   ProfileRange pr("b200_sgemm %dx%dx%d", m, n, k);
   if (int r = check_gemm_args("b200_sgemm", ta, tb, m, n, k, A, lda, B, ldb, C, ldc)) return r;
   if (m == 0 || n == 0) return 0;
@@ -608,6 +626,7 @@ int b200_sgemm(b200_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha, 
 
 int b200_sgemm_prepare(b200_ctx* ctx, int m, int n, int k, int lda, int ldb) {
   B200_REQUIRE(ctx, "b200_sgemm_prepare: null context");
+  DeviceScope ds(ctx->device);
   if (m <= 0 || n <= 0 || k <= 0) return 0;
   return sgemm_tc_prepare(ctx, m, n, k, lda, ldb);
 }
@@ -625,6 +644,7 @@ static int check_gemv_args(const char* who, int trans, int m, int n, const void*
 int b200_dgemv(b200_ctx* ctx, int trans, int m, int n, double alpha, const double* A, int lda,
                const double* x, int incx, double beta, double* y, int incy) {
   B200_REQUIRE(ctx, "b200_dgemv: null context");
+  DeviceScope ds(ctx->device);
   ProfileRange pr("b200_dgemv %dx%d", m, n);
   if (int r = check_gemv_args("b200_dgemv", trans, m, n, A, lda, x, incx, y, incy)) return r;
   if (join_lanes_into_compute(ctx)) return 1;
@@ -634,6 +654,7 @@ int b200_dgemv(b200_ctx* ctx, int trans, int m, int n, double alpha, const doubl
 int b200_sgemv(b200_ctx* ctx, int trans, int m, int n, float alpha, const float* A, int lda,
                const float* x, int incx, float beta, float* y, int incy) {
   B200_REQUIRE(ctx, "b200_sgemv: null context");
+  DeviceScope ds(ctx->device);
   ProfileRange pr("b200_sgemv %dx%d", m, n);
   if (int r = check_gemv_args("b200_sgemv", trans, m, n, A, lda, x, incx, y, incy)) return r;
   if (join_lanes_into_compute(ctx)) return 1;
@@ -699,6 +720,7 @@ template <typename T, typename GemmFn>
 int gemm_offload(b200_ctx* ctx, int m, int n, int k, T alpha, const T* hA, T* dA, int lda,
                  const T* hB, T* dB, int ldb, T beta, T* hC, T* dC, int ldc, GemmFn gemm) {
   B200_REQUIRE(ctx && hA && dA && hB && dB && hC && dC, "gemm_offload: null argument");
+  DeviceScope ds(ctx->device);
   ProfileRange pr("b200_%cgemm_offload %dx%dx%d", sizeof(T) == 8 ? 'd' : 's', m, n, k);
   B200_REQUIRE(m >= 0 && n >= 0 && k >= 0, "gemm_offload: negative dimension");
   if (m == 0 || n == 0) return 0;
@@ -918,6 +940,7 @@ template <typename T, typename GemvFn>
 int gemv_offload(b200_ctx* ctx, int m, int n, T alpha, const T* hA, T* dA, int lda, const T* hx,
                  T* dx, T beta, T* hy, T* dy, GemvFn gemv) {
   B200_REQUIRE(ctx && hA && dA && hx && dx && hy && dy, "gemv_offload: null argument");
+  DeviceScope ds(ctx->device);
   ProfileRange pr("b200_%cgemv_offload %dx%d", sizeof(T) == 8 ? 'd' : 's', m, n);
   B200_REQUIRE(m >= 0 && n >= 0, "gemv_offload: negative dimension");
   if (m == 0) return 0;
@@ -1001,11 +1024,13 @@ unsigned long long b200_launch_count(const b200_ctx* ctx) { return ctx ? ctx->la
 
 int b200_timer_start(b200_ctx* ctx) {
   B200_REQUIRE(ctx, "b200_timer_start: null context");
+  DeviceScope ds(ctx->device);
   B200_CUDA(cudaEventRecord(ctx->t0, ctx->compute));
   return 0;
 }
 int b200_timer_stop(b200_ctx* ctx, float* ms) {
   B200_REQUIRE(ctx && ms, "b200_timer_stop: null argument");
+  DeviceScope ds(ctx->device);
   B200_CUDA(cudaEventRecord(ctx->t1, ctx->compute));
   B200_CUDA(cudaEventSynchronize(ctx->t1));
   B200_CUDA(cudaEventElapsedTime(ms, ctx->t0, ctx->t1));
@@ -1014,6 +1039,7 @@ int b200_timer_stop(b200_ctx* ctx, float* ms) {
 
 int b200_probe_peak(b200_ctx* ctx, const char* which, double* result) {
   B200_REQUIRE(ctx, "b200_probe_peak: null context");
+  DeviceScope ds(ctx->device);
   return probe_peak(ctx, which, result);
 }
 

@@ -74,6 +74,7 @@ struct b200_ctx {
   int opt_sgemm = 0;       // 0 auto, 1 tc, 2 ffma
   int opt_sgemm_streamk = 1;  // CTA-pair SGEMM kernel: 1 stream-K over the partial last wave, 0 whole tiles only
   int opt_sgemm_pair = 0;  // tcgen05 SGEMM tile config: 0 auto, 1 CTA-pair 256x256, 2 single-CTA 128x128
+  int opt_sgemm_fused = 0; // 3xTF32 operand split: 0 auto, 1 fused into the GEMM (converter warps), 2 separate pre-pass
   int opt_dgemm_tile = 0;  // 0 auto, 64, 128
   // Always mode: operand sets up to these sizes are computed in place from pinned host
   // memory (measured break-evens, scripts/zerocopy_ab.sh: GEMM re-reads tiles over PCIe,
@@ -95,6 +96,35 @@ namespace b200 {
 
 // cudaFuncSetAttribute is per device: one-time flags are kept per device id
 constexpr int kMaxDevices = 64;
+
+// Every ABI call runs with its context's device current and hands the calling thread back on
+// the device it came with.  (Allocations and launches bind to the CURRENT device, not to the
+// stream's: after a team call had left the thread on its last member's GPU, a single-GPU
+// context grew its workspace on that GPU and ran its kernels through peer mappings.)  The
+// common case -- already on the right device -- costs one cudaGetDevice.
+struct DeviceScope {
+  int prev = -1;
+  bool changed = false;
+  explicit DeviceScope(int device) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != device) changed = cudaSetDevice(device) == cudaSuccess;
+  }
+  ~DeviceScope() {
+    if (changed) cudaSetDevice(prev);
+  }
+  DeviceScope(const DeviceScope&) = delete;
+  DeviceScope& operator=(const DeviceScope&) = delete;
+};
+// Team calls walk over several devices: put the thread back where it was.
+struct DeviceRestore {
+  int prev = -1;
+  DeviceRestore() {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+  }
+  ~DeviceRestore() {
+    int now = -1;
+    if (prev >= 0 && cudaGetDevice(&now) == cudaSuccess && now != prev) cudaSetDevice(prev);
+  }
+};
 
 int ensure_workspace(b200_ctx* ctx, size_t bytes);
 // Transfer-engine plumbing shared by the single-GPU (b200blas.cu) and multi-GPU (mg.cu) engines.

@@ -146,6 +146,7 @@ int fill_vals(MgMember& me, uint32_t base) {
 int setup_member(b200_mg* mg, int g, int device) {
   MgMember& me = mg->mem[g];
   if (b200_ctx_create(&me.ctx, device)) return 1;
+  B200_CUDA(cudaSetDevice(device));  // the flag page and the push stream live on this member's GPU
   B200_CUDA(cudaMalloc((void**)&me.flags, sizeof(uint32_t) * kFlagWords));
   B200_CUDA(cudaMemset(me.flags, 0, sizeof(uint32_t) * kFlagWords));
   B200_CUDA(cudaMalloc((void**)&me.vals, sizeof(uint32_t) * kValTable));
@@ -571,7 +572,8 @@ int gemv_step(b200_mg* mg, int g, const b200_mg_gemv_args& a) {
   return 0;
 }
 
-void worker_main(MgWorker* w) {
+void worker_main(MgWorker* w, int device) {
+  cudaSetDevice(device);  // this thread only ever drives one member
   std::unique_lock<std::mutex> lk(w->mu);
   for (;;) {
     w->cv.wait(lk, [&] { return w->has_job || w->quit; });
@@ -587,7 +589,8 @@ void worker_main(MgWorker* w) {
 void start_workers(b200_mg* mg) {
   if (mg->self >= 0 || mg->world < 2) return;
   mg->workers = new MgWorker[mg->world];
-  for (int g = 0; g < mg->world; g++) mg->workers[g].th = std::thread(worker_main, &mg->workers[g]);
+  for (int g = 0; g < mg->world; g++)
+    mg->workers[g].th = std::thread(worker_main, &mg->workers[g], mg->mem[g].ctx ? mg->mem[g].ctx->device : 0);
 }
 
 void stop_workers(b200_mg* mg) {
@@ -632,9 +635,6 @@ int run_members(b200_mg* mg, int active, const std::function<int(int)>& fn) {
       set_error("%s", w.err);
     }
   }
-  int dev = 0;
-  if (mg->mem[0].ctx) dev = mg->mem[0].ctx->device;
-  cudaSetDevice(dev);
   return rc;
 }
 
@@ -680,6 +680,7 @@ int b200_mg_active_gemv(int world, int elem, int m, int n) {
 // ------------------------------------------------------------------ teams
 
 int b200_mg_create(b200_mg** out, int ngpus) {
+  DeviceRestore dr;
   B200_REQUIRE(out, "b200_mg_create: out is null");
   *out = nullptr;
   int count = 0;
@@ -691,8 +692,6 @@ int b200_mg_create(b200_mg** out, int ngpus) {
   }
   B200_REQUIRE(ngpus >= 1 && ngpus <= kMaxTeam, "b200_mg_create: ngpus = %d outside [1, %d]", ngpus, kMaxTeam);
   B200_REQUIRE(ngpus <= count, "b200_mg_create: %d GPUs requested, %d visible", ngpus, count);
-  int restore = 0;
-  cudaGetDevice(&restore);
   b200_mg* mg = new b200_mg();
   mg->world = ngpus;
   if (common_init(mg)) { b200_mg_destroy(mg); return 1; }
@@ -718,13 +717,13 @@ int b200_mg_create(b200_mg** out, int ngpus) {
       cudaGetLastError();
     }
   }
-  cudaSetDevice(restore);
   start_workers(mg);
   *out = mg;
   return 0;
 }
 
 int b200_mg_create_rank(b200_mg** out, int device, int rank, int world) {
+  DeviceRestore dr;
   B200_REQUIRE(out, "b200_mg_create_rank: out is null");
   *out = nullptr;
   B200_REQUIRE(world >= 1 && world <= kMaxTeam && rank >= 0 && rank < world,
@@ -738,6 +737,7 @@ int b200_mg_create_rank(b200_mg** out, int device, int rank, int world) {
 }
 
 int b200_mg_destroy(b200_mg* mg) {
+  DeviceRestore dr;
   if (!mg) return 0;
   stop_workers(mg);
   for (int g = 0; g < mg->world; g++) {
@@ -768,6 +768,7 @@ int b200_mg_ctx(b200_mg* mg, int member, b200_ctx** ctx) {
 }
 
 int b200_mg_sync(b200_mg* mg) {
+  DeviceRestore dr;
   B200_REQUIRE(mg, "b200_mg_sync: null team");
   for (int g = 0; g < mg->world; g++)
     if (sync_member(mg->mem[g])) return 1;
@@ -777,6 +778,7 @@ int b200_mg_sync(b200_mg* mg) {
 // ---- rank mode: CUDA IPC plumbing (the caller moves the 64-byte handles between processes)
 
 int b200_mg_export(b200_mg* mg, const void* dev, void* handle64) {
+  DeviceRestore dr;
   B200_REQUIRE(mg && handle64 && mg->self >= 0, "b200_mg_export: needs a rank-mode team");
   B200_CUDA(cudaSetDevice(mg->mem[mg->self].ctx->device));
   static_assert(sizeof(cudaIpcMemHandle_t) == B200_MG_HANDLE_BYTES, "handle size");
@@ -787,6 +789,7 @@ int b200_mg_export(b200_mg* mg, const void* dev, void* handle64) {
 }
 
 int b200_mg_import(b200_mg* mg, int member, const void* handle64, void** dev) {
+  DeviceRestore dr;
   B200_REQUIRE(mg && handle64 && mg->self >= 0 && member >= 0 && member < mg->world && member != mg->self,
                "b200_mg_import: bad argument (member %d)", member);
   B200_CUDA(cudaSetDevice(mg->mem[mg->self].ctx->device));
@@ -804,6 +807,7 @@ int b200_mg_import(b200_mg* mg, int member, const void* handle64, void** dev) {
 }
 
 int b200_mg_unmap(b200_mg* mg, void* dev) {
+  DeviceRestore dr;
   B200_REQUIRE(mg && mg->self >= 0, "b200_mg_unmap: needs a rank-mode team");
   if (dev) B200_CUDA(cudaIpcCloseMemHandle(dev));
   return 0;
@@ -812,23 +816,27 @@ int b200_mg_unmap(b200_mg* mg, void* dev) {
 // ------------------------------------------------------------------ one member's step
 
 int b200_mg_gemm(b200_mg* mg, int member, const b200_mg_gemm_args* args) {
+  DeviceRestore dr;
   B200_REQUIRE(mg && args, "b200_mg_gemm: null argument");
   B200_REQUIRE(args->elem == 4 || args->elem == 8, "b200_mg_gemm: elem must be 4 or 8");
   return args->elem == 8 ? gemm_step<double>(mg, member, *args) : gemm_step<float>(mg, member, *args);
 }
 
 int b200_mg_gemv(b200_mg* mg, int member, const b200_mg_gemv_args* args) {
+  DeviceRestore dr;
   B200_REQUIRE(mg && args, "b200_mg_gemv: null argument");
   B200_REQUIRE(args->elem == 4 || args->elem == 8, "b200_mg_gemv: elem must be 4 or 8");
   return args->elem == 8 ? gemv_step<double>(mg, member, *args) : gemv_step<float>(mg, member, *args);
 }
 
 int b200_mg_gemm_team(b200_mg* mg, const b200_mg_gemm_args* args) {
+  DeviceRestore dr;
   B200_REQUIRE(mg && args, "b200_mg_gemm_team: null argument");
   return run_members(mg, args[0].active, [mg, args](int g) { return b200_mg_gemm(mg, g, &args[g]); });
 }
 
 int b200_mg_gemv_team(b200_mg* mg, const b200_mg_gemv_args* args) {
+  DeviceRestore dr;
   B200_REQUIRE(mg && args, "b200_mg_gemv_team: null argument");
   return run_members(mg, args[0].active, [mg, args](int g) { return b200_mg_gemv(mg, g, &args[g]); });
 }
@@ -840,6 +848,7 @@ int b200_mg_gemv_team(b200_mg* mg, const b200_mg_gemv_args* args) {
 
 int b200_mg_problem_create(b200_mg* mg, int kind, int elem, int mode, int m, int n, int k, void** h0, void** h1,
                            void** h2, b200_mg_problem** out) {
+  DeviceRestore dr;
   B200_REQUIRE(mg && out && h0 && h1 && h2, "b200_mg_problem_create: null argument");
   B200_REQUIRE(mg->self < 0, "b200_mg_problem_create: whole-problem calls need a local team (b200_mg_create)");
   B200_REQUIRE((kind == B200_MG_GEMM || kind == B200_MG_GEMV) && (elem == 4 || elem == 8) && m >= 0 && n >= 0 && k >= 0,
@@ -985,6 +994,7 @@ struct TraceScope {
 };
 
 int b200_mg_problem_preloop(b200_mg_problem* p, double beta) {
+  DeviceRestore dr;
   B200_REQUIRE(p, "b200_mg_problem_preloop: null problem");
   TraceScope ts(p, "preloop");
   b200_mg* mg = p->mg;
@@ -1015,6 +1025,7 @@ int b200_mg_problem_preloop(b200_mg_problem* p, double beta) {
 }
 
 int b200_mg_problem_call(b200_mg_problem* p, double alpha, double beta) {
+  DeviceRestore dr;
   B200_REQUIRE(p, "b200_mg_problem_call: null problem");
   TraceScope ts(p, "call");
   b200_mg* mg = p->mg;
@@ -1054,6 +1065,7 @@ int b200_mg_problem_call(b200_mg_problem* p, double alpha, double beta) {
 }
 
 int b200_mg_problem_postloop(b200_mg_problem* p) {
+  DeviceRestore dr;
   B200_REQUIRE(p, "b200_mg_problem_postloop: null problem");
   TraceScope ts(p, "postloop");
   b200_mg* mg = p->mg;
@@ -1075,6 +1087,7 @@ int b200_mg_problem_postloop(b200_mg_problem* p) {
 }
 
 int b200_mg_problem_destroy(b200_mg_problem* p) {
+  DeviceRestore dr;
   if (!p) return 0;
   b200_mg* mg = p->mg;
   int rc = b200_mg_sync(mg);

@@ -58,7 +58,6 @@ namespace b200 {
 namespace {
 
 constexpr int BM = 128, BN = 128, BK = 32;
-constexpr int STAGES = 3;
 constexpr int ACC_STAGES = 2;
 constexpr int UMMA_K = 8;
 constexpr int KB_PER_CHUNK = 4;  // k-blocks accumulated in TMEM before promotion (K = 128)
@@ -66,10 +65,52 @@ constexpr int NUM_THREADS = 256;
 constexpr uint32_t TMEM_COLS = ACC_STAGES * BN;  // 256 (power of two >= 32)
 constexpr uint32_t A_TILE = BM * BK * 4;         // 16 KB: 4 chunks x [32 k][128 B]
 constexpr uint32_t B_TILE = BN * BK * 4;         // 16 KB: [128 n][128 B]
-constexpr uint32_t STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;
-constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t SLOT = A_TILE + B_TILE;       // one ring slot: an A tile and a B tile, 32 KB
 
 using namespace ptx;
+
+// Shared-memory rings of one CTA (both kernels: the CTA-pair kernel stages 128 rows of A and 128
+// columns of B per CTA too).  The tensor core reads four tiles per k-block: {A_hi, B_hi} from a
+// slot of the hi ring, {A_lo, B_lo} from a slot of the lo ring.
+//   pre-split (FUSED = false)  TMA fills both slots from the hi/lo copies in the workspace; the
+//                              rings advance together (3 + 3 slots = 192 KB).
+//   FUSED                      TMA lands the caller's RAW FP32 tiles in the hi ring (4 slots: TMA
+//                              latency + conversion + MMA are in flight at once) and two converter
+//                              warps write the lo ring (2 slots) from them.
+template <bool FUSED>
+struct Rings {
+  static constexpr int R = FUSED ? 4 : 3;
+  static constexpr int L = FUSED ? 2 : 3;
+  static constexpr uint32_t SMEM = (uint32_t)(R + L) * SLOT + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert(8 * (2 * R + 2 * L + 2 * ACC_STAGES + 1) <= 256, "barrier area");
+  uint32_t base, bars;
+  __device__ explicit Rings(const uint8_t* smem_raw) {
+    base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-byte alignment
+    bars = base + (uint32_t)(R + L) * SLOT;
+  }
+  __device__ uint32_t a_hi(int r) const { return base + (uint32_t)r * SLOT; }
+  __device__ uint32_t b_hi(int r) const { return a_hi(r) + A_TILE; }
+  __device__ uint32_t a_lo(int l) const { return base + (uint32_t)(R + l) * SLOT; }
+  __device__ uint32_t b_lo(int l) const { return a_lo(l) + A_TILE; }
+  // hi_full: TMA bytes have landed (pre-split: of all four tiles); hi_empty / lo_empty: the MMAs that
+  // read the slot are done; lo_full (FUSED): the converter warps have written the slot
+  __device__ uint32_t hi_full(int r) const { return bars + 8u * r; }
+  __device__ uint32_t hi_empty(int r) const { return bars + 8u * (R + r); }
+  __device__ uint32_t lo_full(int l) const { return bars + 8u * (2 * R + l); }
+  __device__ uint32_t lo_empty(int l) const { return bars + 8u * (2 * R + L + l); }
+  __device__ uint32_t tfull(int a) const { return bars + 8u * (2 * R + 2 * L + a); }
+  __device__ uint32_t tempty(int a) const { return bars + 8u * (2 * R + 2 * L + ACC_STAGES + a); }
+  __device__ uint32_t tmem_slot() const { return bars + 8u * (2 * R + 2 * L + 2 * ACC_STAGES); }
+};
+// position in a ring of N slots + the mbarrier phase that goes with it
+struct Pos {
+  int i = 0;
+  uint32_t ph = 0;
+  template <int N>
+  __device__ __forceinline__ void next() {
+    if (++i == N) { i = 0; ph ^= 1; }
+  }
+};
 
 // UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start>>4  [16,30) LBO>>4  [32,46) SBO>>4  [46,48) version=1  [61,64) layout type
@@ -87,7 +128,7 @@ constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (0
 // ------------------------------------------------------------------ kernels
 
 // x = hi + lo with hi = RN_tf32(x) (13 low bits zero), lo = x - hi (exact).  One launch
-// splits both operands: blocks [0, blocks_a) take A, the rest take B.
+// splits both operands: blocks [0, blocks_a) take A, the rest take B.  (Pre-split path only.)
 __device__ __forceinline__ void split_tf32_range(const float* __restrict__ src, float* __restrict__ hi,
                                                  float* __restrict__ lo, size_t count, int block, int blocks) {
   const size_t n4 = count / 4;
@@ -121,6 +162,57 @@ split_tf32_kernel(const float* __restrict__ a, float* __restrict__ a_hi, float* 
     split_tf32_range(b, b_hi, b_lo, count_b, blockIdx.x - blocks_a, gridDim.x - blocks_a);
 }
 
+// ---- fused operand split (FUSED kernels) ----------------------------------------------------
+// TMA lands the RAW FP32 tile in the hi ring: tcgen05 kind::tf32 reads only the top 19 bits of
+// each word, so the raw word IS hi = trunc_tf32(x).  Two converter warps then write
+// lo = RN_tf32(x - trunc_tf32(x)) word for word at the same offset of a lo-ring slot -- the
+// subtraction is exact in FP32 (lo < 2^-10 |x|, <= 13 significant bits), the rounding to TF32's
+// 11 bits is what the tensor core would otherwise do by truncation (a one-sided error), and the
+// same offset means whatever swizzle TMA applied carries over untouched.  No pre-pass over A
+// and B, no hi/lo copies in HBM, no workspace.
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128f(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float tf32_lo(float x) {
+  const float lo = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  return __uint_as_float((__float_as_uint(lo) + 0x1000u) & 0xFFFFE000u);
+}
+// The SLOT bytes of raw words at `src` -> their lo parts at `dst`; thread `t` of 64.  Batches of
+// four 16-byte words, software-pipelined by hand: the loads of batch b + 1 are in flight while
+// batch b is converted and stored (the asm statements are volatile, so the order written here is
+// the order issued -- a plain unrolled loop serialised load -> convert -> store on one register set).
+__device__ __forceinline__ void convert_slot(uint32_t src, uint32_t dst, int t) {
+  constexpr uint32_t STEP = 64u * 16u;  // a warp touches 512 consecutive bytes: conflict-free
+  constexpr int U = 4, BATCHES = (int)(SLOT / STEP) / U;
+  const uint32_t s0 = src + (uint32_t)t * 16u, d0 = dst + (uint32_t)t * 16u;
+  float4 cur[U], nxt[U];
+#pragma unroll
+  for (int u = 0; u < U; u++) cur[u] = lds128f(s0 + u * STEP);
+#pragma unroll
+  for (int b = 0; b < BATCHES; b++) {
+    if (b + 1 < BATCHES) {
+#pragma unroll
+      for (int u = 0; u < U; u++) nxt[u] = lds128f(s0 + ((b + 1) * U + u) * STEP);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      cur[u].x = tf32_lo(cur[u].x); cur[u].y = tf32_lo(cur[u].y);
+      cur[u].z = tf32_lo(cur[u].z); cur[u].w = tf32_lo(cur[u].w);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) sts128f(d0 + (b * U + u) * STEP, cur[u]);
+#pragma unroll
+    for (int u = 0; u < U; u++) cur[u] = nxt[u];
+  }
+}
+// generic-proxy writes -> visible to the tensor core's (async proxy) reads
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // Store one thread's row of `NCOL` column results: C[row, col0 + j] = alpha * sum[j] (+ beta * C).
 // The per-column work is kept to a multiply, an address step and the store: guards and the
 // beta test are hoisted (ncu on M = N = 8192, K = 32: the epilogue warps were issue-latency
@@ -144,24 +236,21 @@ __device__ __forceinline__ void store_row(float* __restrict__ cp, long long ldc,
   }
 }
 
+// FUSED: map_a_hi / map_b_hi describe the caller's A and B themselves; the lo maps are unused.
+template <bool FUSED>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                     const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                     int m, int n, int k, float alpha, float beta, float* __restrict__ C, long long ldc,
                     int tiles_m, int tiles_n, int splits, int kb_per_split, float* __restrict__ partial,
                     unsigned int* __restrict__ counters) {
+  using RG = Rings<FUSED>;
+  constexpr int R = RG::R, L = RG::L;
   extern __shared__ uint8_t smem_raw[];
   __shared__ int s_is_last;
-  // SWIZZLE_128B atoms need 1024-byte alignment
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bars = base + STAGES * STAGE_BYTES;
-  auto full_bar = [&](int s) { return bars + 8u * s; };
-  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
-  auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + ACC_STAGES + a); };
-  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 2 * ACC_STAGES);
+  const RG rg(smem_raw);
   volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (rg.tmem_slot() - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // work item = (tile, k split): item / splits is the tile, item % splits the k range
@@ -173,17 +262,21 @@ sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
   };
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; s++) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+    for (int s = 0; s < R; s++) {
+      mbar_init(rg.hi_full(s), 1);
+      mbar_init(rg.hi_empty(s), 1);
+    }
+    for (int s = 0; s < L; s++) {
+      mbar_init(rg.lo_full(s), 2);  // one arrive per converter warp
+      mbar_init(rg.lo_empty(s), 1);
     }
     for (int a = 0; a < ACC_STAGES; a++) {
-      mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
+      mbar_init(rg.tfull(a), 1);
+      mbar_init(rg.tempty(a), 4);  // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 2) tmem_alloc(rg.tmem_slot(), TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -201,27 +294,24 @@ sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+      Pos r;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         int m0, n0, kb_lo, kb_hi;
         tile_coords(item / splits, m0, n0);
         kb_range(item, kb_lo, kb_hi);
         for (int kb = kb_lo; kb < kb_hi; kb++) {
-          mbar_wait(empty_bar(stage), phase ^ 1);
-          const uint32_t sa_hi = base + stage * STAGE_BYTES;
-          const uint32_t sa_lo = sa_hi + A_TILE;
-          const uint32_t sb_hi = sa_lo + A_TILE;
-          const uint32_t sb_lo = sb_hi + B_TILE;
-          mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+          mbar_wait(rg.hi_empty(r.i), r.ph ^ 1);
+          const uint32_t bar = rg.hi_full(r.i);
+          mbar_expect_tx(bar, FUSED ? SLOT : 2 * SLOT);
 #pragma unroll
-          for (int c = 0; c < BM / 32; c++) {
-            tma_load_2d(sa_hi + c * 4096, &map_a_hi, full_bar(stage), m0 + c * 32, kb * BK);
-            tma_load_2d(sa_lo + c * 4096, &map_a_lo, full_bar(stage), m0 + c * 32, kb * BK);
+          for (int c = 0; c < BM / 32; c++) tma_load_2d(rg.a_hi(r.i) + c * 4096, &map_a_hi, bar, m0 + c * 32, kb * BK);
+          tma_load_2d(rg.b_hi(r.i), &map_b_hi, bar, kb * BK, n0);
+          if (!FUSED) {  // R == L: the rings advance together
+#pragma unroll
+            for (int c = 0; c < BM / 32; c++) tma_load_2d(rg.a_lo(r.i) + c * 4096, &map_a_lo, bar, m0 + c * 32, kb * BK);
+            tma_load_2d(rg.b_lo(r.i), &map_b_lo, bar, kb * BK, n0);
           }
-          tma_load_2d(sb_hi, &map_b_hi, full_bar(stage), kb * BK, n0);
-          tma_load_2d(sb_lo, &map_b_lo, full_bar(stage), kb * BK, n0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          r.next<R>();
         }
       }
     }
@@ -233,23 +323,21 @@ sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     // each chunk into round-to-nearest FP32 registers while the next chunk runs in
     // the other accumulator stage.
     if (lane == 0) {
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
+      Pos r, l, acc;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         int kb_lo, kb_hi;
         kb_range(item, kb_lo, kb_hi);
         for (int kb0 = kb_lo; kb0 < kb_hi; kb0 += KB_PER_CHUNK) {
-          mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+          mbar_wait(rg.tempty(acc.i), acc.ph ^ 1);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * BN;
+          const uint32_t d_tmem = tmem_base + acc.i * BN;
           const int kb1 = min(kb_hi, kb0 + KB_PER_CHUNK);
           for (int kb = kb0; kb < kb1; kb++) {
-            mbar_wait(full_bar(stage), phase);
+            mbar_wait(rg.hi_full(r.i), r.ph);  // the TMA writes (FUSED: the converters saw them too)
+            if (FUSED) mbar_wait(rg.lo_full(l.i), l.ph);
             tc_fence_after();
-            const uint32_t sa_hi = base + stage * STAGE_BYTES;
-            const uint32_t sa_lo = sa_hi + A_TILE;
-            const uint32_t sb_hi = sa_lo + A_TILE;
-            const uint32_t sb_lo = sb_hi + B_TILE;
+            const int li = FUSED ? l.i : r.i;
+            const uint32_t sa_hi = rg.a_hi(r.i), sb_hi = rg.b_hi(r.i), sa_lo = rg.a_lo(li), sb_lo = rg.b_lo(li);
 #pragma unroll
             for (int ks = 0; ks < BK / UMMA_K; ks++) {
               const uint64_t a_hi = umma_desc(sa_hi + ks * 1024, 4096, 512, kSwizzle128B_Base32B);
@@ -260,20 +348,43 @@ sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
               umma_tf32(d_tmem, a_hi, b_lo, kIdesc, 1);
               umma_tf32(d_tmem, a_hi, b_hi, kIdesc, 1);
             }
-            umma_commit(empty_bar(stage));  // frees the smem stage when these MMAs finish
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            umma_commit(rg.hi_empty(r.i));  // frees the slot(s) when these MMAs finish
+            if (FUSED) {
+              umma_commit(rg.lo_empty(l.i));
+              l.next<L>();
+            }
+            r.next<R>();
           }
-          umma_commit(tfull_bar(acc));  // chunk complete -> epilogue promotes it
-          if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+          umma_commit(rg.tfull(acc.i));  // chunk complete -> epilogue promotes it
+          acc.next<ACC_STAGES>();
         }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp < 4) {
+    // ===================== converters (FUSED): lo ring <- hi ring =====================
+    if (FUSED) {
+      const int ct = threadIdx.x - 64;  // 0..63
+      Pos r, l;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        int kb_lo, kb_hi;
+        kb_range(item, kb_lo, kb_hi);
+        for (int kb = kb_lo; kb < kb_hi; kb++) {
+          mbar_wait(rg.hi_full(r.i), r.ph);
+          mbar_wait(rg.lo_empty(l.i), l.ph ^ 1);
+          convert_slot(rg.a_hi(r.i), rg.a_lo(l.i), ct);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(rg.lo_full(l.i));
+          r.next<R>();
+          l.next<L>();
+        }
+      }
+    }
+  } else {
     // ===================== epilogue =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int et = threadIdx.x - 128;  // 0..127 among the epilogue threads
-    int acc = 0;
-    uint32_t acc_phase = 0;
+    Pos acc;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       const int tile = item / splits;
       int m0, n0, kb_lo, kb_hi;
@@ -283,9 +394,9 @@ sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
 #pragma unroll
       for (int j = 0; j < BN; j++) sum[j] = 0.0f;
       for (int kb0 = kb_lo; kb0 < kb_hi; kb0 += KB_PER_CHUNK) {
-        mbar_wait(tfull_bar(acc), acc_phase);
+        mbar_wait(rg.tfull(acc.i), acc.ph);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+        const uint32_t taddr = tmem_base + acc.i * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll
         for (int c0 = 0; c0 < BN; c0 += 32) {
           float v[32];
@@ -295,8 +406,8 @@ sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));
-        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        if (lane == 0) mbar_arrive(rg.tempty(acc.i));
+        acc.next<ACC_STAGES>();
       }
       if (splits == 1) {
         const int row = m0 + q * 32 + lane;
@@ -327,8 +438,8 @@ sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
       __threadfence();
       // thread = 4 consecutive rows (one float4) x 32 columns: 32 independent 16-byte loads
       // in flight per split
-      const int rg = et & 31, cg = et >> 5;
-      const float* src = partial + (size_t)tile * (BM * BN) + (size_t)(cg * 32) * BM + rg * 4;
+      const int rg4 = et & 31, cg = et >> 5;
+      const float* src = partial + (size_t)tile * (BM * BN) + (size_t)(cg * 32) * BM + rg4 * 4;
       const size_t zstride = (size_t)(tiles_m * tiles_n) * (BM * BN);
       float4 tot[32];
 #pragma unroll
@@ -340,16 +451,16 @@ sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
           tot[j].x += v.x; tot[j].y += v.y; tot[j].z += v.z; tot[j].w += v.w;
         }
       }
-      const int row0 = m0 + rg * 4;
+      const int row0 = m0 + rg4 * 4;
 #pragma unroll
       for (int j = 0; j < 32; j++) {
         const int col = n0 + cg * 32 + j;
         if (col >= n) continue;
         float* cp = C + row0 + (long long)col * ldc;
-        const float r[4] = {tot[j].x, tot[j].y, tot[j].z, tot[j].w};
+        const float rr[4] = {tot[j].x, tot[j].y, tot[j].z, tot[j].w};
 #pragma unroll
         for (int e = 0; e < 4; e++)
-          if (row0 + e < m) cp[e] = (beta == 0.0f) ? alpha * r[e] : alpha * r[e] + beta * cp[e];
+          if (row0 + e < m) cp[e] = (beta == 0.0f) ? alpha * rr[e] : alpha * rr[e] + beta * cp[e];
       }
     }
   }
@@ -367,14 +478,18 @@ sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
 // stalls there (ncu: tensor pipe 74 % active).  Pairing the two SMs of a TPC
 // (tcgen05 cta_group::2) makes one UMMA M = 256, N = 256: each CTA still feeds its
 // own 128 rows of A, but only HALF of B's columns (the hardware shares B between the
-// pair), so a 128-clock UMMA reads 4 + 4 KB per SM = 64 B/clk and TMA adds 43 B/clk.
+// pair), so a 128-clock UMMA reads 4 + 4 KB per SM = 64 B/clk and TMA adds 43 B/clk
+// (FUSED: TMA 21 B/clk + the converters' 21 B/clk of reads and 21 B/clk of writes).
 //
 //   cluster (2,1,1), 384 threads per CTA:
-//     warp 0      TMA producer: own rows of A_hi/A_lo, own column half of B_hi/B_lo;
-//                 bytes of BOTH CTAs are counted on the LEADER's full barrier
+//     warp 0      TMA producer: own rows of A, own column half of B.  Pre-split: hi and lo
+//                 tiles, bytes of BOTH CTAs counted on the LEADER's hi_full barrier.  FUSED: raw
+//                 tiles, bytes counted on the CTA's own hi_full barrier (its converters wait there)
 //     warp 1      MMA issuer (leader CTA only); tcgen05.commit multicasts the
-//                 "stage free" / "chunk ready" arrivals to both CTAs
-//     warp 2      TMEM allocator (all 512 columns: 2 accumulator stages x 256)
+//                 "slot free" / "chunk ready" arrivals to both CTAs
+//     warps 2-3   (warp 2: TMEM allocator, all 512 columns = 2 accumulator stages x 256)
+//                 FUSED: converters; the four converter warps of the pair arrive on the LEADER's
+//                 lo_full barrier (the leader's MMAs read both CTAs' slots)
 //     warps 4-11  epilogue: lane quarter = warp % 4, column half = (warp - 4) / 4,
 //                 128 running sums per thread (registers moved over with setmaxnreg)
 namespace pair {
@@ -386,30 +501,26 @@ constexpr int CTA_N = PAIR_N / 2;     // columns of B each CTA stages
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = 128 + 32 * EPI_WARPS;
 constexpr uint32_t TMEM_COLS2 = ACC_STAGES * PAIR_N;  // 512
-constexpr uint32_t A_TILE2 = CTA_M * BK * 4;          // 16 KB
-constexpr uint32_t B_TILE2 = CTA_N * BK * 4;          // 16 KB
-constexpr uint32_t STAGE_BYTES2 = 2 * A_TILE2 + 2 * B_TILE2;
-constexpr uint32_t SMEM_BYTES2 = STAGES * STAGE_BYTES2 + 1024 + 256;
+static_assert(CTA_M * BK * 4 == A_TILE && CTA_N * BK * 4 == B_TILE, "the pair kernel shares Rings<> with the single-CTA kernel");
 constexpr uint32_t kIdesc2 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (0u << 16) |
                              ((uint32_t)(PAIR_N >> 3) << 17) | ((uint32_t)(PAIR_M >> 4) << 24);
 
+template <bool FUSED>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                          const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                          int m, int n, int k, float alpha, float beta, float* __restrict__ C, long long ldc,
                          int tiles_m, int tiles_n, int raster_group, int sk_tiles, int sk_slots,
                          float* __restrict__ partial, unsigned int* __restrict__ counters) {
+  using RG = Rings<FUSED>;
+  constexpr int R = RG::R, L = RG::L;
   extern __shared__ uint8_t smem_raw[];
   __shared__ int s_is_last;
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bars = base + STAGES * STAGE_BYTES2;
-  auto full_bar = [&](int s) { return bars + 8u * s; };                              // leader's is used
-  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };                  // one per CTA
-  auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };              // one per CTA
-  auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + ACC_STAGES + a); };  // leader's is used
-  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 2 * ACC_STAGES);
+  const RG rg(smem_raw);
+  // pre-split: the leader's hi_full is used (both CTAs' bytes); hi_empty / lo_empty / tfull: one per
+  // CTA (multicast commits); tempty and (FUSED) lo_full: the leader's are used
   volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (rg.tmem_slot() - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -429,7 +540,6 @@ sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
   auto sk_begin = [&](int p) { return (long long)p * sk_units / num_pairs; };
   auto sk_pair_of = [&](long long u) { return (int)(((u + 1) * num_pairs - 1) / sk_units); };
   struct Item { int tile, c0, c1; };
-  // iterate: call with it = -1 first; returns false when this pair has no more work
   long long sk_u = 0, sk_end = 0;
   int dp_next = pair_id;
   bool sk_started = false;
@@ -454,17 +564,21 @@ sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
   };
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; s++) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+    for (int s = 0; s < R; s++) {
+      mbar_init(rg.hi_full(s), 1);
+      mbar_init(rg.hi_empty(s), 1);
+    }
+    for (int s = 0; s < L; s++) {
+      mbar_init(rg.lo_full(s), 4);  // two converter warps in each CTA of the pair
+      mbar_init(rg.lo_empty(s), 1);
     }
     for (int a = 0; a < ACC_STAGES; a++) {
-      mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 2 * EPI_WARPS);  // every epilogue warp of both CTAs
+      mbar_init(rg.tfull(a), 1);
+      mbar_init(rg.tempty(a), 2 * EPI_WARPS);  // every epilogue warp of both CTAs
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) tmem_alloc_2sm(tmem_slot, TMEM_COLS2);
+  if (warp == 2) tmem_alloc_2sm(rg.tmem_slot(), TMEM_COLS2);
   tc_fence_before();
   __syncwarp();
   cluster_sync();
@@ -484,8 +598,7 @@ sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
     setmaxnreg_dec<48>();
     if (warp == 0 && lane == 0) {
       // ===================== TMA producer (both CTAs) =====================
-      int stage = 0;
-      uint32_t phase = 0;
+      Pos r, l;
       Item w;
       while (next_item(w)) {
         int m0, n0;
@@ -493,48 +606,56 @@ sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
         const int my_m = m0 + (int)rank * CTA_M, my_n = n0 + (int)rank * CTA_N;
         const int kb_hi = min(num_kb, w.c1 * KB_PER_CHUNK);
         for (int kb = w.c0 * KB_PER_CHUNK; kb < kb_hi; kb++) {
-          mbar_wait(empty_bar(stage), phase ^ 1);
-          const uint32_t sa_hi = base + stage * STAGE_BYTES2;
-          const uint32_t sa_lo = sa_hi + A_TILE2;
-          const uint32_t sb_hi = sa_lo + A_TILE2;
-          const uint32_t sb_lo = sb_hi + B_TILE2;
-          if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * STAGE_BYTES2);
-          const uint32_t lbar = mapa_shared(full_bar(stage), 0);
+          mbar_wait(rg.hi_empty(r.i), r.ph ^ 1);
+          if (FUSED) {
+            const uint32_t bar = rg.hi_full(r.i);
+            mbar_expect_tx(bar, SLOT);
 #pragma unroll
-          for (int c = 0; c < CTA_M / 32; c++) {
-            tma_load_2d_2sm(sa_hi + c * 4096, &map_a_hi, lbar, my_m + c * 32, kb * BK);
-            tma_load_2d_2sm(sa_lo + c * 4096, &map_a_lo, lbar, my_m + c * 32, kb * BK);
+            for (int c = 0; c < CTA_M / 32; c++) tma_load_2d(rg.a_hi(r.i) + c * 4096, &map_a_hi, bar, my_m + c * 32, kb * BK);
+            tma_load_2d(rg.b_hi(r.i), &map_b_hi, bar, kb * BK, my_n);
+            l.next<L>();
+          } else {
+            if (rank == 0) mbar_expect_tx(rg.hi_full(r.i), 4 * SLOT);
+            const uint32_t lbar = mapa_shared(rg.hi_full(r.i), 0);
+#pragma unroll
+            for (int c = 0; c < CTA_M / 32; c++) {
+              tma_load_2d_2sm(rg.a_hi(r.i) + c * 4096, &map_a_hi, lbar, my_m + c * 32, kb * BK);
+              tma_load_2d_2sm(rg.a_lo(r.i) + c * 4096, &map_a_lo, lbar, my_m + c * 32, kb * BK);
+            }
+            tma_load_2d_2sm(rg.b_hi(r.i), &map_b_hi, lbar, kb * BK, my_n);
+            tma_load_2d_2sm(rg.b_lo(r.i), &map_b_lo, lbar, kb * BK, my_n);
           }
-          tma_load_2d_2sm(sb_hi, &map_b_hi, lbar, kb * BK, my_n);
-          tma_load_2d_2sm(sb_lo, &map_b_lo, lbar, kb * BK, my_n);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          r.next<R>();
         }
       }
-      // tail: every stage this CTA filled has been released, i.e. no UMMA still reads
+      // tail: every slot this CTA filled has been released, i.e. no UMMA still reads
       // this CTA's shared memory and no multicast arrival is still in flight to it
-      for (int s = 0; s < STAGES; s++) {
-        mbar_wait(empty_bar(stage), phase ^ 1);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      for (int s = 0; s < R; s++) {
+        mbar_wait(rg.hi_empty(r.i), r.ph ^ 1);
+        r.next<R>();
       }
+      if (FUSED)
+        for (int s = 0; s < L; s++) {
+          mbar_wait(rg.lo_empty(l.i), l.ph ^ 1);
+          l.next<L>();
+        }
     } else if (warp == 1 && rank == 0 && lane == 0) {
       // ===================== MMA issuer (leader CTA) =====================
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
+      Pos r, l, acc;
       Item w;
       while (next_item(w)) {
         for (int ch = w.c0; ch < w.c1; ch++) {
           const int kb0 = ch * KB_PER_CHUNK;
-          mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+          mbar_wait(rg.tempty(acc.i), acc.ph ^ 1);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * PAIR_N;
+          const uint32_t d_tmem = tmem_base + acc.i * PAIR_N;
           const int kb1 = min(num_kb, kb0 + KB_PER_CHUNK);
           for (int kb = kb0; kb < kb1; kb++) {
-            mbar_wait(full_bar(stage), phase);
+            mbar_wait(rg.hi_full(r.i), r.ph);  // FUSED: this CTA's raw tiles; the peer's are behind lo_full
+            if (FUSED) mbar_wait(rg.lo_full(l.i), l.ph);
             tc_fence_after();
-            const uint32_t sa_hi = base + stage * STAGE_BYTES2;
-            const uint32_t sa_lo = sa_hi + A_TILE2;
-            const uint32_t sb_hi = sa_lo + A_TILE2;
-            const uint32_t sb_lo = sb_hi + B_TILE2;
+            const int li = FUSED ? l.i : r.i;
+            const uint32_t sa_hi = rg.a_hi(r.i), sb_hi = rg.b_hi(r.i), sa_lo = rg.a_lo(li), sb_lo = rg.b_lo(li);
 #pragma unroll
             for (int ks = 0; ks < BK / UMMA_K; ks++) {
               const uint64_t a_hi = umma_desc(sa_hi + ks * 1024, 4096, 512, kSwizzle128B_Base32B);
@@ -545,11 +666,37 @@ sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
               umma_tf32_2sm(d_tmem, a_hi, b_lo, kIdesc2, 1);
               umma_tf32_2sm(d_tmem, a_hi, b_hi, kIdesc2, 1);
             }
-            umma_commit_2sm(empty_bar(stage), 3);  // frees this stage in both CTAs
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            umma_commit_2sm(rg.hi_empty(r.i), 3);  // frees the slot(s) in both CTAs
+            if (FUSED) {
+              umma_commit_2sm(rg.lo_empty(l.i), 3);
+              l.next<L>();
+            }
+            r.next<R>();
           }
-          umma_commit_2sm(tfull_bar(acc), 3);  // chunk complete -> both CTAs' epilogues
-          if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+          umma_commit_2sm(rg.tfull(acc.i), 3);  // chunk complete -> both CTAs' epilogues
+          acc.next<ACC_STAGES>();
+        }
+      }
+    } else if (FUSED && warp >= 2) {
+      // ===================== converters (both CTAs): lo ring <- hi ring =====================
+      const int ct = threadIdx.x - 64;  // 0..63
+      const uint32_t leader_lo_full0 = mapa_shared(rg.lo_full(0), 0);
+      Pos r, l;
+      Item w;
+      while (next_item(w)) {
+        const int kb_hi = min(num_kb, w.c1 * KB_PER_CHUNK);
+        for (int kb = w.c0 * KB_PER_CHUNK; kb < kb_hi; kb++) {
+          mbar_wait(rg.hi_full(r.i), r.ph);
+          mbar_wait(rg.lo_empty(l.i), l.ph ^ 1);
+          convert_slot(rg.a_hi(r.i), rg.a_lo(l.i), ct);
+          fence_proxy_async_smem();
+          __syncwarp();
+          // what must be ordered before the leader's MMAs are this warp's shared-memory stores, and
+          // fence.proxy.async has done that; the arrive itself is only the signal (ptx.cuh:
+          // a cluster-scope release would add a MEMBAR.GPU to every k-block)
+          if (lane == 0) mbar_arrive_cluster(leader_lo_full0 + 8u * l.i);
+          r.next<R>();
+          l.next<L>();
         }
       }
     }
@@ -561,9 +708,8 @@ sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
     const int q = warp & 3;           // TMEM lane quarter this warp may access
     const int half = (warp - 4) >> 2; // which 128 of the 256 accumulator columns
     const int et = threadIdx.x - 128; // 0..255 among the epilogue threads of this CTA
-    const uint32_t leader_tempty0 = mapa_shared(tempty_bar(0), 0);
-    int acc = 0;
-    uint32_t acc_phase = 0;
+    const uint32_t leader_tempty0 = mapa_shared(rg.tempty(0), 0);
+    Pos acc;
     Item w;
     while (next_item(w)) {
       int m0, n0;
@@ -572,9 +718,9 @@ sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
 #pragma unroll
       for (int j = 0; j < CTA_N; j++) sum[j] = 0.0f;
       for (int ch = w.c0; ch < w.c1; ch++) {
-        mbar_wait(tfull_bar(acc), acc_phase);
+        mbar_wait(rg.tfull(acc.i), acc.ph);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + acc * PAIR_N + half * CTA_N + ((uint32_t)(q * 32) << 16);
+        const uint32_t taddr = tmem_base + acc.i * PAIR_N + half * CTA_N + ((uint32_t)(q * 32) << 16);
 #pragma unroll
         for (int c0 = 0; c0 < CTA_N; c0 += 32) {
           float v[32];
@@ -584,8 +730,8 @@ sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(leader_tempty0 + 8u * acc);
-        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        if (lane == 0) mbar_arrive_cluster(leader_tempty0 + 8u * acc.i);
+        acc.next<ACC_STAGES>();
       }
       const int trow = (int)rank * CTA_M + q * 32 + lane;  // row inside the 256 x 256 tile
       if (w.c0 == 0 && w.c1 == chunks) {
@@ -619,8 +765,8 @@ sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
       __threadfence();
       // this CTA finishes the WHOLE tile (both halves): thread = 4 consecutive rows x 64 columns,
       // two passes of 32 columns, 32 independent 16-byte loads in flight per contributor
-      const int rg = et & 63, cg = et >> 6;
-      const int row0 = m0 + rg * 4;
+      const int rg4 = et & 63, cg = et >> 6;
+      const int row0 = m0 + rg4 * 4;
 #pragma unroll 1
       for (int pass = 0; pass < 2; pass++) {
         const int cbase = cg * 64 + pass * 32;
@@ -628,7 +774,7 @@ sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
 #pragma unroll
         for (int j = 0; j < 32; j++) tot[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int z = 0; z < ncontrib; z++) {
-          const float* src = slots + (size_t)z * (PAIR_M * PAIR_N) + (size_t)cbase * PAIR_M + rg * 4;
+          const float* src = slots + (size_t)z * (PAIR_M * PAIR_N) + (size_t)cbase * PAIR_M + rg4 * 4;
 #pragma unroll
           for (int j = 0; j < 32; j++) {
             const float4 v = __ldcg(reinterpret_cast<const float4*>(src + j * PAIR_M));
@@ -640,10 +786,10 @@ sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
           const int col = n0 + cbase + j;
           if (col >= n) continue;
           float* cp = C + row0 + (long long)col * ldc;
-          const float r[4] = {tot[j].x, tot[j].y, tot[j].z, tot[j].w};
+          const float rr[4] = {tot[j].x, tot[j].y, tot[j].z, tot[j].w};
 #pragma unroll
           for (int e = 0; e < 4; e++)
-            if (row0 + e < m) cp[e] = (beta == 0.0f) ? alpha * r[e] : alpha * r[e] + beta * cp[e];
+            if (row0 + e < m) cp[e] = (beta == 0.0f) ? alpha * rr[e] : alpha * rr[e] + beta * cp[e];
         }
       }
     }
@@ -665,6 +811,16 @@ std::atomic<int> g_pair_max_clusters_dev[kMaxDevices] = {};
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Tensor maps depend only on the operand addresses and the shape: the harness' ten back-to-back
+// calls encode them once; the multi-GPU engine walks a handful of K-chunks of A per step.
+struct MapSet {
+  const void *pa = nullptr, *pb = nullptr;  // what a_hi / b_hi describe
+  int device = -1, m = -1, n = -1, k = -1, lda = -1, ldb = -1;
+  bool fused = false;
+  CUtensorMap a_hi, a_lo, b_hi, b_lo;
+};
+constexpr int kMapSets = 8;
+
 }  // namespace
 
 int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const float* A, int lda,
@@ -672,14 +828,9 @@ int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const flo
   if (ctx->opt_sgemm == 2) return -1;  // "ffma" forces the SIMT path, "tc" forces this one
   const bool forced = ctx->opt_sgemm == 1;
   if ((lda % 4) || (ldb % 4) || ((uintptr_t)A % 16) || ((uintptr_t)B % 16)) return -1;
-  // below ~512^3 the three launches (two operand splits + GEMM) and four descriptor
-  // encodes cost more than the FFMA path's single launch (measured crossover, size_sweep.py)
+  // below ~512^3 the launch and the descriptor encodes cost more than the FFMA path's single
+  // launch (measured crossover, size_sweep.py)
   if (!forced && ((double)m * n * k < 1.0e8 || m < 64 || n < 64)) return -1;
-
-  const size_t countA = (size_t)lda * (k - 1) + m, countB = (size_t)ldb * (n - 1) + k;
-  const size_t offAlo = align_up(countA * 4, 1024), offBhi = 2 * offAlo;
-  const size_t offBlo = offBhi + align_up(countB * 4, 1024);
-  const size_t need = offBlo + align_up(countB * 4, 1024);
   // ---- schedule: CTA pairs on 256 x 256 tiles, or single CTAs on 128 x 128 tiles cut into
   // `splits` k ranges.  Both are persistent, so time = waves x time per work item; the cost
   // model below is in tensor-pipe clocks per k-block of 32 (pair UMMA 256x256x8: 128 clk x 12 =
@@ -718,57 +869,28 @@ int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const flo
   kb_per_split = (kb_per_split + KB_PER_CHUNK - 1) / KB_PER_CHUNK * KB_PER_CHUNK;
   splits = (total_kb + kb_per_split - 1) / kb_per_split;
   const size_t part_bytes = splits > 1 ? (size_t)splits * tiles1 * BM * BN * sizeof(float) : 0;
-  // + room for the pair kernel's stream-K slots: rem tiles x (pairs / rem + 2) contributors x 256 KB
-  // = (pairs + 2 rem) x 256 KB <= 56 MB whatever the problem size; b200_alloc pre-sizes the workspace
-  // for it so that this call does not reallocate inside a timed region
-  const int pairs_est = std::max(1, P / 2);
-  const size_t sk_room = (size_t)(pairs_est + 2 * (int)(tiles2 % pairs_est)) * pair::PAIR_M * pair::PAIR_N * sizeof(float);
-  if (ensure_workspace(ctx, need + std::max(part_bytes, sk_room))) return 1;
-  char* ws = (char*)ctx->workspace;
-  float *a_hi = (float*)ws, *a_lo = (float*)(ws + offAlo), *b_hi = (float*)(ws + offBhi),
-        *b_lo = (float*)(ws + offBlo);
-
-  // The four tensor maps depend only on the workspace address and the shape: ten
-  // back-to-back calls of the harness loop encode them once.
-  struct MapCache {
-    const void* ws = nullptr;
-    int device = -1, m = -1, n = -1, k = -1, lda = -1, ldb = -1;
-    CUtensorMap a_hi, a_lo, b_hi, b_lo;
-  };
-  static thread_local MapCache mc;
-  if (mc.ws != ws || mc.device != ctx->device || mc.m != m || mc.n != n || mc.k != k || mc.lda != lda || mc.ldb != ldb) {
-    mc.ws = nullptr;
-    if (make_tensor_map_2d(&mc.a_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, a_hi, m, k, (uint64_t)lda * 4, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 2;
-    if (make_tensor_map_2d(&mc.a_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, a_lo, m, k, (uint64_t)lda * 4, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 2;
-    if (make_tensor_map_2d(&mc.b_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, b_hi, k, n, (uint64_t)ldb * 4, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B)) return 2;
-    if (make_tensor_map_2d(&mc.b_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, b_lo, k, n, (uint64_t)ldb * 4, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B)) return 2;
-    mc.ws = ws; mc.device = ctx->device; mc.m = m; mc.n = n; mc.k = k; mc.lda = lda; mc.ldb = ldb;
-  }
-  const CUtensorMap &ma_hi = mc.a_hi, &ma_lo = mc.a_lo, &mb_hi = mc.b_hi, &mb_lo = mc.b_lo;
-
-  {
-    const int split_blocks = ctx->sm_count * 8;
-    int blocks_a = (int)((double)split_blocks * (double)countA / (double)(countA + countB));
-    blocks_a = std::max(1, std::min(split_blocks - 1, blocks_a));
-    split_tf32_kernel<<<split_blocks, 256, 0, ctx->compute>>>(A, a_hi, a_lo, countA, B, b_hi, b_lo, countB, blocks_a);
-    B200_CUDA(cudaGetLastError());
-  }
 
   std::atomic<bool>& g_pair_attr_done = g_pair_attr_done_dev[ctx->device % kMaxDevices];
   std::atomic<int>& g_pair_max_clusters = g_pair_max_clusters_dev[ctx->device % kMaxDevices];
   if (!g_pair_attr_done) {
-    B200_CUDA(cudaFuncSetAttribute(pair::sgemm_3xtf32_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)pair::SMEM_BYTES2));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * ctx->sm_count, 1, 1);
-    cfg.blockDim = dim3(pair::THREADS, 1, 1);
-    cfg.dynamicSmemBytes = pair::SMEM_BYTES2;
-    int clusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&clusters, pair::sgemm_3xtf32_pair_kernel, &cfg) != cudaSuccess || clusters <= 0) {
-      cudaGetLastError();
-      clusters = ctx->sm_count / 2;
-    }
-    g_pair_max_clusters = std::min(clusters, ctx->sm_count / 2);
+    int pairs_min = ctx->sm_count / 2;
+    auto setup = [&](auto kernel, uint32_t smem) -> int {
+      B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2 * ctx->sm_count, 1, 1);
+      cfg.blockDim = dim3(pair::THREADS, 1, 1);
+      cfg.dynamicSmemBytes = smem;
+      int clusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&clusters, kernel, &cfg) != cudaSuccess || clusters <= 0) {
+        cudaGetLastError();
+        clusters = ctx->sm_count / 2;
+      }
+      pairs_min = std::min(pairs_min, clusters);
+      return 0;
+    };
+    if (setup(pair::sgemm_3xtf32_pair_kernel<false>, Rings<false>::SMEM)) return 1;
+    if (setup(pair::sgemm_3xtf32_pair_kernel<true>, Rings<true>::SMEM)) return 1;
+    g_pair_max_clusters = pairs_min;
     g_pair_attr_done = true;
   }
   const int pairs = g_pair_max_clusters;
@@ -778,7 +900,7 @@ int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const flo
   // partial-tile fix-up costs (>= 35 us and >= 3 % of the run; measured: 2304^3 159 -> 143 us,
   // 2560^3 176 -> 158, 4096^3 548 -> 521, while a predicted saving of 26 us at 2816^3 was a 3 us loss).
   int sk_tiles = 0, sk_slots = 0;
-  float* sk_partial = nullptr;
+  size_t sk_bytes = 0;
   const int chunks = (total_kb + KB_PER_CHUNK - 1) / KB_PER_CHUNK;
   if (ctx->opt_sgemm_streamk && tiles2 > 0) {
     const int rem = (int)(tiles2 % pairs);
@@ -786,12 +908,10 @@ int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const flo
     const long long seg = units / pairs;
     const double saved_us = (double)(chunks - (units + pairs - 1) / pairs) * 3.2;
     const double total_us = (double)waves(tiles2, pairs) * chunks * 3.2;
-    const size_t bytes = (size_t)rem * (size_t)(seg > 0 ? chunks / seg + 2 : 0) * pair::PAIR_M * pair::PAIR_N * sizeof(float);
-    if (rem > 0 && seg >= 1 && saved_us >= 35.0 && saved_us >= 0.03 * total_us && rem <= ctx->num_counters &&
-        need + bytes <= ctx->workspace_bytes) {
+    if (rem > 0 && seg >= 1 && saved_us >= 35.0 && saved_us >= 0.03 * total_us && rem <= ctx->num_counters) {
       sk_tiles = rem;
       sk_slots = (int)(chunks / seg) + 2;
-      sk_partial = (float*)(ws + need);
+      sk_bytes = (size_t)rem * (size_t)sk_slots * pair::PAIR_M * pair::PAIR_N * sizeof(float);
     }
   }
   const double cost2 = sk_tiles ? ((double)tiles2 * total_kb / pairs) * 1536.0 + 2 * 2500.0 + 15000.0
@@ -800,40 +920,124 @@ int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const flo
   if (ctx->opt_sgemm_pair == 1) use_pair = true;
   if (ctx->opt_sgemm_pair == 2) use_pair = false;
 
+  // ---- operand split: fused into the GEMM (converter warps: one launch, no hi/lo copies in HBM)
+  // or a separate pass writing hi/lo copies into the workspace.  Fused wins wherever the launch
+  // and the extra pass over A and B matter or the CTA-pair kernel runs (measured, fused vs
+  // pre-split: 2048^3 74.9 vs 84.4 us, 4096^3 485 vs 523, 8192x512x512 27.5 vs 35.9,
+  // 16384x4096x16384 7.93 vs 8.12 ms, 8192^3 a tie).  The one exception is the single-CTA kernel
+  // on a long K range: it is already bound by shared-memory bandwidth (the UMMAs alone read
+  // 128 B/clk) and the converters' traffic comes on top (1280^3 41.7 vs 38.3 us, 1536^3 49.6 vs 45.4).
+  bool fused = ctx->opt_sgemm_fused != 2;
+  if (ctx->opt_sgemm_fused == 0 && !use_pair && splits == 1 && total_kb >= 32) fused = false;
+
+  const size_t countA = (size_t)lda * (k - 1) + m, countB = (size_t)ldb * (n - 1) + k;
+  const size_t offAlo = align_up(countA * 4, 1024), offBhi = 2 * offAlo;
+  const size_t offBlo = offBhi + align_up(countB * 4, 1024);
+  const size_t need = fused ? 0 : offBlo + align_up(countB * 4, 1024);
+  // room for the pair kernel's stream-K slots: rem tiles x (pairs / rem + 2) contributors x 256 KB
+  // = (pairs + 2 rem) x 256 KB <= 56 MB whatever the problem size; the context reserves that much
+  // when it is created (and b200_sgemm_prepare the pre-split copies), so that this call does not
+  // reallocate inside a timed region
+  if (ensure_workspace(ctx, need + std::max(part_bytes, sk_bytes))) return 1;
+  char* ws = (char*)ctx->workspace;
+  float *a_hi = (float*)ws, *a_lo = (float*)(ws + offAlo), *b_hi = (float*)(ws + offBhi),
+        *b_lo = (float*)(ws + offBlo);
+  float* sk_partial = sk_tiles ? (float*)(ws + need) : nullptr;
+  const float* pa = fused ? A : a_hi;  // what the hi maps describe
+  const float* pb = fused ? B : b_hi;
+
+  static thread_local MapSet sets[kMapSets];
+  static thread_local int next_set = 0;
+  MapSet* mc = nullptr;
+  for (int i = 0; i < kMapSets; i++) {
+    MapSet& s = sets[i];
+    if (s.pa == pa && s.pb == pb && s.device == ctx->device && s.fused == fused && s.m == m && s.n == n && s.k == k &&
+        s.lda == lda && s.ldb == ldb) {
+      mc = &s;
+      break;
+    }
+  }
+  if (!mc) {
+    mc = &sets[next_set];
+    next_set = (next_set + 1) % kMapSets;
+    mc->pa = nullptr;
+    if (make_tensor_map_2d(&mc->a_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, pa, m, k, (uint64_t)lda * 4, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 2;
+    if (make_tensor_map_2d(&mc->b_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, pb, k, n, (uint64_t)ldb * 4, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B)) return 2;
+    if (fused) {
+      mc->a_lo = mc->a_hi;
+      mc->b_lo = mc->b_hi;
+    } else {
+      if (make_tensor_map_2d(&mc->a_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, a_lo, m, k, (uint64_t)lda * 4, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 2;
+      if (make_tensor_map_2d(&mc->b_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, b_lo, k, n, (uint64_t)ldb * 4, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B)) return 2;
+    }
+    mc->pa = pa; mc->pb = pb; mc->device = ctx->device; mc->fused = fused;
+    mc->m = m; mc->n = n; mc->k = k; mc->lda = lda; mc->ldb = ldb;
+  }
+  const CUtensorMap &ma_hi = mc->a_hi, &ma_lo = mc->a_lo, &mb_hi = mc->b_hi, &mb_lo = mc->b_lo;
+
+  if (!fused) {
+    const int split_blocks = ctx->sm_count * 8;
+    int blocks_a = (int)((double)split_blocks * (double)countA / (double)(countA + countB));
+    blocks_a = std::max(1, std::min(split_blocks - 1, blocks_a));
+    split_tf32_kernel<<<split_blocks, 256, 0, ctx->compute>>>(A, a_hi, a_lo, countA, B, b_hi, b_lo, countB, blocks_a);
+    B200_CUDA(cudaGetLastError());
+  }
+
   if (use_pair) {
     static const char* rg_env = getenv("B200_SGEMM_RASTER");  // tuning: m-tiles per raster group
     const int raster_group = rg_env ? std::max(1, atoi(rg_env)) : 8;
     const int grid = 2 * (int)(sk_tiles ? pairs : std::min<long long>(tiles2, pairs));
-    pair::sgemm_3xtf32_pair_kernel<<<grid, pair::THREADS, pair::SMEM_BYTES2, ctx->compute>>>(
-        ma_hi, ma_lo, mb_hi, mb_lo, m, n, k, alpha, beta, C, (long long)ldc, (int)t2m, (int)t2n, raster_group,
-        sk_tiles, sk_slots, sk_partial, ctx->counters);
+    if (fused)
+      pair::sgemm_3xtf32_pair_kernel<true><<<grid, pair::THREADS, Rings<true>::SMEM, ctx->compute>>>(
+          ma_hi, ma_lo, mb_hi, mb_lo, m, n, k, alpha, beta, C, (long long)ldc, (int)t2m, (int)t2n, raster_group,
+          sk_tiles, sk_slots, sk_partial, ctx->counters);
+    else
+      pair::sgemm_3xtf32_pair_kernel<false><<<grid, pair::THREADS, Rings<false>::SMEM, ctx->compute>>>(
+          ma_hi, ma_lo, mb_hi, mb_lo, m, n, k, alpha, beta, C, (long long)ldc, (int)t2m, (int)t2n, raster_group,
+          sk_tiles, sk_slots, sk_partial, ctx->counters);
     B200_CUDA(cudaGetLastError());
-    note_launch(ctx, sk_tiles ? "sgemm_3xtf32_tcgen05_pair_256x256x32_streamk" : "sgemm_3xtf32_tcgen05_pair_256x256x32", 2);
+    if (fused)
+      note_launch(ctx, sk_tiles ? "sgemm_3xtf32_fused_tcgen05_pair_256x256x32_streamk" : "sgemm_3xtf32_fused_tcgen05_pair_256x256x32", 1);
+    else
+      note_launch(ctx, sk_tiles ? "sgemm_3xtf32_tcgen05_pair_256x256x32_streamk" : "sgemm_3xtf32_tcgen05_pair_256x256x32", 2);
     return 0;
   }
   std::atomic<bool>& g_attr_done = g_attr_done_dev[ctx->device % kMaxDevices];
   if (!g_attr_done) {
-    B200_CUDA(cudaFuncSetAttribute(sgemm_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)SMEM_BYTES));
+    B200_CUDA(cudaFuncSetAttribute(sgemm_3xtf32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)Rings<false>::SMEM));
+    B200_CUDA(cudaFuncSetAttribute(sgemm_3xtf32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)Rings<true>::SMEM));
     g_attr_done = true;
   }
   float* partial = splits > 1 ? (float*)(ws + need) : nullptr;
   const int grid = (int)std::min<long long>(tiles1 * splits, ctx->sm_count);
-  sgemm_3xtf32_kernel<<<grid, NUM_THREADS, SMEM_BYTES, ctx->compute>>>(
-      ma_hi, ma_lo, mb_hi, mb_lo, m, n, k, alpha, beta, C, (long long)ldc, (int)t1m, (int)t1n, splits,
-      kb_per_split, partial, ctx->counters);
+  if (fused)
+    sgemm_3xtf32_kernel<true><<<grid, NUM_THREADS, Rings<true>::SMEM, ctx->compute>>>(
+        ma_hi, ma_lo, mb_hi, mb_lo, m, n, k, alpha, beta, C, (long long)ldc, (int)t1m, (int)t1n, splits,
+        kb_per_split, partial, ctx->counters);
+  else
+    sgemm_3xtf32_kernel<false><<<grid, NUM_THREADS, Rings<false>::SMEM, ctx->compute>>>(
+        ma_hi, ma_lo, mb_hi, mb_lo, m, n, k, alpha, beta, C, (long long)ldc, (int)t1m, (int)t1n, splits,
+        kb_per_split, partial, ctx->counters);
   B200_CUDA(cudaGetLastError());
-  note_launch(ctx, splits > 1 ? "sgemm_3xtf32_tcgen05_128x128x32_splitk" : "sgemm_3xtf32_tcgen05_128x128x32", 2);
+  if (fused)
+    note_launch(ctx, splits > 1 ? "sgemm_3xtf32_fused_tcgen05_128x128x32_splitk" : "sgemm_3xtf32_fused_tcgen05_128x128x32", 1);
+  else
+    note_launch(ctx, splits > 1 ? "sgemm_3xtf32_tcgen05_128x128x32_splitk" : "sgemm_3xtf32_tcgen05_128x128x32", 2);
   return 0;
 }
 
-// Scratch one SGEMM of this shape will need (the four TF32 split operands + partial-tile room),
-// reserved outside the caller's timed region.
+// Scratch one SGEMM of this shape will need (pre-split path: the four TF32 split operands;
+// always: partial-tile room), reserved outside the caller's timed region.
 int sgemm_tc_prepare(b200_ctx* ctx, int m, int n, int k, int lda, int ldb) {
   if (ctx->opt_sgemm == 2 || (lda % 4) || (ldb % 4) || m < 64 || n < 64 || k < 1) return 0;
   if (ctx->opt_sgemm != 1 && (double)m * n * k < 1.0e8) return 0;
-  const size_t countA = (size_t)lda * (k - 1) + m, countB = (size_t)ldb * (n - 1) + k;
-  const size_t need = 2 * align_up(countA * 4, 1024) + 2 * align_up(countB * 4, 1024);
+  size_t need = 0;
+  if (ctx->opt_sgemm_fused == 2) {
+    const size_t countA = (size_t)lda * (k - 1) + m, countB = (size_t)ldb * (n - 1) + k;
+    need = 2 * align_up(countA * 4, 1024) + 2 * align_up(countB * 4, 1024);
+  }
   return ensure_workspace(ctx, need + ((size_t)64 << 20));
 }
 

@@ -168,6 +168,59 @@ def test_one_member_team_matches_oracle(blob, oracle, kind, dims, mode):
     assert max_rel_err(got, want) <= TOL[dt], (kind, dims, mode)
 
 
+def test_team_calls_leave_the_callers_device_alone(blob, oracle):
+    """A team walks over its members' GPUs; the calling thread must come back on the device it
+    had.  (Regression: b200_mg_destroy left the thread on the LAST member's GPU, the session's
+    single-GPU context then grew its workspace there and ran through peer mappings.)"""
+    import torch
+    need_gpus(2)
+    before = torch.cuda.current_device()
+    with blob.Team(ngpus=2) as team:
+        assert torch.cuda.current_device() == before
+        m, n, k = 1024, 1024, 512
+        A, B, _ = oracle.init_gemm("f64", m, n, k)
+        p = team.problem(blob.MG_GEMM, "f64", MODES["always"], m, n, k)
+        p.host[0][:], p.host[1][:], p.host[2][:] = A, B, 0
+        p.preloop(); p.call(); p.postloop()
+        assert torch.cuda.current_device() == before
+        p.destroy()
+        assert torch.cuda.current_device() == before
+    assert torch.cuda.current_device() == before
+
+
+def test_context_calls_run_on_their_own_device_whatever_is_current(blob, ctx, oracle):
+    """Allocations and launches bind to the CURRENT device: every ABI call selects its
+    context's device and puts the caller's back."""
+    import torch
+    need_gpus(2)
+    m, n, k = 2304, 2304, 2304  # SGEMM: pair kernel + stream-K partials in the workspace
+    A, B, _ = oracle.init_gemm("f32", m, n, k)
+    dA = torch.from_numpy(A).cuda(0)
+    dB = torch.from_numpy(B).cuda(0)
+    C1 = torch.zeros(m * n, dtype=torch.float32, device="cuda:0")
+    C2 = torch.zeros_like(C1)
+    torch.cuda.synchronize()
+    ctx.gemm("f32", m, n, k, 1.0, dA, m, dB, k, 0.0, C1, m)
+    ctx.sync()
+    try:
+        torch.cuda.set_device(1)
+        ctx.gemm("f32", m, n, k, 1.0, dA, m, dB, k, 0.0, C2, m)
+        h, d = ctx.alloc(blob.OFFLOAD_ONCE, 1 << 20)      # must land on the context's GPU
+        assert torch.cuda.current_device() == 1
+        ctx.sync()
+        try:
+            from cuda.bindings import runtime as cudart
+        except ImportError:
+            cudart = None
+        if cudart is not None:
+            err, attr = cudart.cudaPointerGetAttributes(d if isinstance(d, int) else d.value)
+            assert int(err) == 0 and attr.device == 0, (err, attr.device)
+        ctx.free(blob.OFFLOAD_ONCE, h, d)
+    finally:
+        torch.cuda.set_device(0)
+    assert torch.equal(C1, C2)
+
+
 # --------------------------------------------------------------- local teams: per-member steps
 
 @pytest.mark.parametrize("wait", ["memop", "kernel"])

@@ -11,12 +11,15 @@ from test_gpu_parity import run_gemm
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True)
-def force_tensor_core_path(ctx):
+@pytest.fixture(autouse=True, params=["fused", "presplit"])
+def force_tensor_core_path(ctx, request):
     """Small shapes default to the FFMA path (launch-latency crossover ~512^3);
-    these tests pin the tcgen05 kernel itself."""
+    these tests pin the tcgen05 kernel itself -- once with the operand split fused into the
+    GEMM (converter warps, the default) and once with the separate pre-split pass."""
     ctx.set_option("sgemm", "tc")
-    yield
+    ctx.set_option("sgemm_fused", "on" if request.param == "fused" else "off")
+    yield request.param
+    ctx.set_option("sgemm_fused", "auto")
     ctx.set_option("sgemm", "auto")
 
 SHAPES = [
@@ -27,12 +30,13 @@ SHAPES = [
 
 
 @pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
-def test_sgemm_tensor_core_path(blob, ctx, oracle, shape):
+def test_sgemm_tensor_core_path(blob, ctx, oracle, shape, force_tensor_core_path):
     m, n, k = shape
     A, B, _ = oracle.init_gemm("f32", m, n, k)
     want = oracle.harness_gemm("f32", m, n, k)
     got, kern = run_gemm(blob, ctx, "f32", "once", m, n, k, A, B, iters=2)
     assert "tcgen05" in kern, kern
+    assert ("fused" in kern) == (force_tensor_core_path == "fused"), kern
     err = max_rel_err(got, want)
     assert err <= 1e-5, (shape, kern, err)
 
@@ -119,6 +123,34 @@ def test_sgemm_pair_matches_single_cta_bitwise(blob, ctx, oracle, force_pair):
     got1, kern1 = run_gemm(blob, ctx, "f32", "once", m, n, k, A, B)
     assert "pair" in kern2 and kern1.endswith("128x128x32"), (kern1, kern2)
     assert np.array_equal(got1, got2)
+
+
+def test_sgemm_fused_split_leaves_no_launch_and_no_workspace_copy(blob, ctx, oracle, force_tensor_core_path):
+    """Fused: ONE launch per SGEMM (no split_tf32_kernel); pre-split: two."""
+    m, n, k = 1024, 768, 512
+    A, B, _ = oracle.init_gemm("f32", m, n, k)
+    l0 = ctx.launch_count()
+    _, kern = run_gemm(blob, ctx, "f32", "once", m, n, k, A, B, iters=1)
+    per_call = ctx.launch_count() - l0
+    assert per_call == (1 if force_tensor_core_path == "fused" else 2), (kern, per_call)
+
+
+def test_sgemm_fused_handles_denormals_zeros_and_negative_values(blob, ctx, oracle, force_tensor_core_path):
+    """lo = RN_tf32(x - trunc_tf32(x)) must be exact-enough for every sign / magnitude mix."""
+    rng = np.random.default_rng(12)
+    m, n, k = 256, 256, 200
+    A = (rng.standard_normal(m * k) * 10.0 ** rng.integers(-6, 6, m * k)).astype(np.float32)
+    B = (rng.standard_normal(k * n) * 10.0 ** rng.integers(-6, 6, k * n)).astype(np.float32)
+    A[::7] = 0.0
+    B[::5] = 0.0
+    A[3::11] = np.float32(1e-41)  # denormal
+    want = np.zeros(m * n, np.float32)
+    oracle.gemm("f32", m, n, k, 1.0, A, m, B, k, 0.0, want, m)
+    bound = np.zeros(m * n, np.float32)
+    oracle.gemm("f32", m, n, k, 1.0, np.abs(A), m, np.abs(B), k, 0.0, bound, m)
+    got, kern = run_gemm(blob, ctx, "f32", "once", m, n, k, A, B)
+    assert "tcgen05" in kern, kern
+    assert float(np.max(np.abs(got.astype(np.float64) - want) / np.maximum(bound, 1e-30))) <= 1e-5
 
 
 @pytest.mark.parametrize("shape", [(128, 128, 8192), (512, 512, 8192), (384, 260, 4100), (200, 130, 2052)],
