@@ -290,6 +290,8 @@ int b200_ctx_create(b200_ctx** out, int device) {
   if (const char* e = getenv("B200_SGEMM")) ctx->opt_sgemm = !strcmp(e, "tc") ? 1 : !strcmp(e, "ffma") ? 2 : 0;
   if (const char* e = getenv("B200_SGEMM_STREAMK")) ctx->opt_sgemm_streamk = strcmp(e, "off") != 0 && strcmp(e, "0") != 0;
   if (const char* e = getenv("B200_SGEMM_PAIR")) ctx->opt_sgemm_pair = !strcmp(e, "on") ? 1 : !strcmp(e, "off") ? 2 : 0;
+  if (const char* e = getenv("B200_SGEMM_TMA_STORE")) ctx->opt_sgemm_tma_store = strcmp(e, "off") != 0 && strcmp(e, "0") != 0;
+  if (const char* e = getenv("B200_TALLK")) ctx->opt_tallk = strcmp(e, "off") != 0 && strcmp(e, "0") != 0;
   if (const char* e = getenv("B200_SGEMM_FUSED")) ctx->opt_sgemm_fused = !strcmp(e, "on") ? 1 : !strcmp(e, "off") ? 2 : 0;
   if (const char* e = getenv("B200_ZEROCOPY_GEMM_BYTES")) ctx->opt_zerocopy_gemm_bytes = (size_t)atoll(e);
   if (const char* e = getenv("B200_ZEROCOPY_GEMV_BYTES")) ctx->opt_zerocopy_gemv_bytes = (size_t)atoll(e);
@@ -360,6 +362,18 @@ int b200_ctx_set_option(b200_ctx* ctx, const char* key, const char* value) {
     else if (!strcmp(value, "on")) ctx->opt_sgemm_pair = 1;
     else if (!strcmp(value, "off")) ctx->opt_sgemm_pair = 2;
     else B200_REQUIRE(false, "b200_ctx_set_option: sgemm_pair must be auto|on|off, got '%s'", value);
+    return 0;
+  }
+  if (!strcmp(key, "sgemm_tma_store")) {
+    if (!strcmp(value, "on") || !strcmp(value, "auto")) ctx->opt_sgemm_tma_store = 1;
+    else if (!strcmp(value, "off")) ctx->opt_sgemm_tma_store = 0;
+    else B200_REQUIRE(false, "b200_ctx_set_option: sgemm_tma_store must be on|off, got '%s'", value);
+    return 0;
+  }
+  if (!strcmp(key, "tallk")) {
+    if (!strcmp(value, "on") || !strcmp(value, "auto")) ctx->opt_tallk = 1;
+    else if (!strcmp(value, "off")) ctx->opt_tallk = 0;
+    else B200_REQUIRE(false, "b200_ctx_set_option: tallk must be on|off, got '%s'", value);
     return 0;
   }
   if (!strcmp(key, "sgemm_fused")) {
@@ -603,7 +617,9 @@ int b200_dgemm(b200_ctx* ctx, int ta, int tb, int m, int n, int k, double alpha,
   if (m == 0 || n == 0) return 0;
   if (join_lanes_into_compute(ctx)) return 1;
   if (!ta && !tb && k > 0 && alpha != 0.0) {
-    const int r = dgemm_dmma_dispatch(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+    int r = gemm_tallk_dispatch<double>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+    if (r >= 0) return r;
+    r = dgemm_dmma_dispatch(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
     if (r >= 0) return r;
   }
   return gemm_simt_dispatch<double>(ctx, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
@@ -618,7 +634,9 @@ int b200_sgemm(b200_ctx* ctx, int ta, int tb, int m, int n, int k, float alpha, 
   if (m == 0 || n == 0) return 0;
   if (join_lanes_into_compute(ctx)) return 1;
   if (!ta && !tb && k > 0 && alpha != 0.0f) {
-    const int r = sgemm_tc_dispatch(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+    int r = gemm_tallk_dispatch<float>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+    if (r >= 0) return r;
+    r = sgemm_tc_dispatch(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
     if (r >= 0) return r;
   }
   return gemm_simt_dispatch<float>(ctx, ta, tb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);

@@ -74,6 +74,7 @@ struct b200_ctx {
   int opt_sgemm = 0;       // 0 auto, 1 tc, 2 ffma
   int opt_sgemm_streamk = 1;  // CTA-pair SGEMM kernel: 1 stream-K over the partial last wave, 0 whole tiles only
   int opt_sgemm_pair = 0;  // tcgen05 SGEMM tile config: 0 auto, 1 CTA-pair 256x256, 2 single-CTA 128x128
+  int opt_sgemm_tma_store = 1;  // tcgen05 SGEMM epilogue: 1 staged through shared memory + TMA store when C allows, 0 register stores
   int opt_sgemm_fused = 0; // 3xTF32 operand split: 0 auto, 1 fused into the GEMM (converter warps), 2 separate pre-pass
   int opt_dgemm_tile = 0;  // 0 auto, 64, 128
   // Always mode: operand sets up to these sizes are computed in place from pinned host
@@ -81,6 +82,7 @@ struct b200_ctx {
   // GEMV touches every element once)
   size_t opt_zerocopy_gemm_bytes = 200u << 10;
   size_t opt_zerocopy_gemv_bytes = 16u << 20;
+  int opt_tallk = 1;       // M, N <= 32 with K >= 1024: the cluster / DSMEM split-K kernel (gemm_tallk.cu); 0 = the generic split-K paths
   int opt_dgemm_min = 32;  // smallest m, n the DMMA kernels take (one 32x32 tile; below: DFMA SIMT path)
   int opt_dgemm_streamk = 1;  // 1: stream-K over the partial last wave of the TMA kernel, 0: whole tiles only
   int opt_dgemm_tma = 1;   // 1: large aligned DGEMMs use the TMA-fed kernel, 0: cp.async kernel
@@ -172,6 +174,12 @@ int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha,
                       float beta, float* C, int ldc);
 
 int sgemm_tc_prepare(b200_ctx* ctx, int m, int n, int k, int lda, int ldb);
+
+// One 32 x 32 tile of C, long K (the reference's M = N = 32 problem type): clusters of 8 CTAs,
+// reduction through distributed shared memory; returns -1 if the shape is not eligible.
+template <typename T>
+int gemm_tallk_dispatch(b200_ctx* ctx, int m, int n, int k, T alpha, const T* A, int lda, const T* B, int ldb, T beta,
+                        T* C, int ldc);
 
 int probe_peak(b200_ctx* ctx, const char* which, double* result);
 

@@ -294,10 +294,10 @@ int gemm_step(b200_mg* mg, int g, const b200_mg_gemm_args& a) {
   // ---- column pieces of my slab (uploads, downloads and gathers overlap compute piece by piece)
   int ns = 1;
   if (upl || down || gather) ns = mg->opt_pieces ? mg->opt_pieces : (int)std::max(1, std::min(kMaxPieces, n / 512));
-  // every SGEMM call splits its operands into TF32 hi/lo first (a pass over all of A per piece):
-  // few pieces, or that pass costs more than the overlap returns (8 GPUs, 32768^3, device
-  // resident: 1404 TFLOP/s with 2 pieces)
-  if (sizeof(T) == 4 && !mg->opt_pieces) ns = (upl || down) ? std::min(ns, 2) : 1;
+  // pre-split SGEMM (sgemm_fused = off) splits its operands into TF32 hi/lo first, a pass over all
+  // of A per piece: few pieces then, or that pass costs more than the overlap returns.  The fused
+  // kernels (the default) have no such pass and take the same pieces as DGEMM.
+  if (sizeof(T) == 4 && !mg->opt_pieces && ctx->opt_sgemm_fused == 2) ns = (upl || down) ? std::min(ns, 2) : 1;
   long long pj0[kMaxPieces], pnc[kMaxPieces];
   for (int j = 0; j < ns; j++) split(n, ns, j, 128, &pj0[j], &pnc[j]);
 

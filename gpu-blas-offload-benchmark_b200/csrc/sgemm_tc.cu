@@ -62,10 +62,12 @@ constexpr int ACC_STAGES = 2;
 constexpr int UMMA_K = 8;
 constexpr int KB_PER_CHUNK = 4;  // k-blocks accumulated in TMEM before promotion (K = 128)
 constexpr int NUM_THREADS = 256;
+constexpr int SINGLE_EPI_WARPS = 4;  // single-CTA kernel: warps 4-7
 constexpr uint32_t TMEM_COLS = ACC_STAGES * BN;  // 256 (power of two >= 32)
 constexpr uint32_t A_TILE = BM * BK * 4;         // 16 KB: 4 chunks x [32 k][128 B]
 constexpr uint32_t B_TILE = BN * BK * 4;         // 16 KB: [128 n][128 B]
 constexpr uint32_t SLOT = A_TILE + B_TILE;       // one ring slot: an A tile and a B tile, 32 KB
+constexpr uint32_t STAGING_PER_WARP = 4096;      // epilogue: two half-buffers of [16 columns][32 rows] floats
 
 using namespace ptx;
 
@@ -81,13 +83,17 @@ template <bool FUSED>
 struct Rings {
   static constexpr int R = FUSED ? 4 : 3;
   static constexpr int L = FUSED ? 2 : 3;
-  static constexpr uint32_t SMEM = (uint32_t)(R + L) * SLOT + 1024 /*align*/ + 256 /*barriers*/;
+  // + 4 KB per epilogue warp: the staging buffers of the TMA-store epilogue (store_rows_tma)
+  static constexpr uint32_t smem_bytes(int epi_warps) {
+    return (uint32_t)(R + L) * SLOT + 1024 /*align*/ + 256 /*barriers*/ + (uint32_t)epi_warps * STAGING_PER_WARP;
+  }
   static_assert(8 * (2 * R + 2 * L + 2 * ACC_STAGES + 1) <= 256, "barrier area");
   uint32_t base, bars;
   __device__ explicit Rings(const uint8_t* smem_raw) {
     base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-byte alignment
     bars = base + (uint32_t)(R + L) * SLOT;
   }
+  __device__ uint32_t staging(int epi_warp) const { return bars + 256u + (uint32_t)epi_warp * STAGING_PER_WARP; }
   __device__ uint32_t a_hi(int r) const { return base + (uint32_t)r * SLOT; }
   __device__ uint32_t b_hi(int r) const { return a_hi(r) + A_TILE; }
   __device__ uint32_t a_lo(int l) const { return base + (uint32_t)(R + l) * SLOT; }
@@ -210,8 +216,6 @@ __device__ __forceinline__ void convert_slot(uint32_t src, uint32_t dst, int t) 
     for (int u = 0; u < U; u++) cur[u] = nxt[u];
   }
 }
-// generic-proxy writes -> visible to the tensor core's (async proxy) reads
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // Store one thread's row of `NCOL` column results: C[row, col0 + j] = alpha * sum[j] (+ beta * C).
 // The per-column work is kept to a multiply, an address step and the store: guards and the
@@ -236,11 +240,43 @@ __device__ __forceinline__ void store_row(float* __restrict__ cp, long long ldc,
   }
 }
 
+// The same row block through shared memory and the TMA store engine (beta == 0, C and ldc
+// 16-byte aligned): the warp writes alpha * sum as [16 columns][32 rows] into one of its two
+// 2 KB half-buffers -- lanes = consecutive rows = consecutive words, conflict-free -- and one
+// lane hands the box to cp.async.bulk.tensor (SASS UTMASTG), which clips at C's bounds.  Per
+// 16 columns the warp issues 16 shared-memory stores and ONE bulk store instead of 16 global
+// stores per lane, and is free for the next tile's tcgen05.ld while the engine drains the box
+// (M = N = 8192, K = 32: the epilogue is all there is).
+__device__ __forceinline__ void sts32f(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+template <int NCOL>
+__device__ __forceinline__ void store_rows_tma(const CUtensorMap* map_c, uint32_t buf, int lane, int row0, int col0,
+                                               int m, int n, const float (&sum)[NCOL], float alpha) {
+  if (row0 >= m) return;
+#pragma unroll
+  for (int s = 0; s < NCOL / 16; s++) {
+    if (col0 + s * 16 >= n) break;
+    const uint32_t half = buf + (uint32_t)(s & 1) * 2048u;
+    if (lane == 0) bulk_wait_read<1>();  // the box that used this half two slices ago has been read
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 16; j++) sts32f(half + j * 128 + lane * 4, alpha * sum[s * 16 + j]);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(map_c, half, row0, col0 + s * 16);
+      bulk_commit();
+    }
+  }
+}
+
 // FUSED: map_a_hi / map_b_hi describe the caller's A and B themselves; the lo maps are unused.
 template <bool FUSED>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                     const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                    const __grid_constant__ CUtensorMap map_c, int tma_c,
                     int m, int n, int k, float alpha, float beta, float* __restrict__ C, long long ldc,
                     int tiles_m, int tiles_n, int splits, int kb_per_split, float* __restrict__ partial,
                     unsigned int* __restrict__ counters) {
@@ -411,7 +447,10 @@ sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
       }
       if (splits == 1) {
         const int row = m0 + q * 32 + lane;
-        if (row < m) store_row<BN>(C + row + (long long)n0 * ldc, ldc, sum, n - n0, alpha, beta);
+        if (tma_c)
+          store_rows_tma<BN>(&map_c, rg.staging(warp - 4), lane, m0 + q * 32, n0, m, n, sum, alpha);
+        else if (row < m)
+          store_row<BN>(C + row + (long long)n0 * ldc, ldc, sum, n - n0, alpha, beta);
         continue;
       }
       // ---- split-K: publish this k range's partial tile ([column][row], rows contiguous);
@@ -463,6 +502,7 @@ sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
           if (row0 + e < m) cp[e] = (beta == 0.0f) ? alpha * rr[e] : alpha * rr[e] + beta * cp[e];
       }
     }
+    if (tma_c && lane == 0) bulk_wait_read<0>();  // the staging buffers outlive their last bulk store
   }
 
   tc_fence_before();
@@ -509,6 +549,7 @@ template <bool FUSED>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                          const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                         const __grid_constant__ CUtensorMap map_c, int tma_c,
                          int m, int n, int k, float alpha, float beta, float* __restrict__ C, long long ldc,
                          int tiles_m, int tiles_n, int raster_group, int sk_tiles, int sk_slots,
                          float* __restrict__ partial, unsigned int* __restrict__ counters) {
@@ -737,7 +778,10 @@ sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
       if (w.c0 == 0 && w.c1 == chunks) {
         const int row = m0 + trow;
         const int col0 = n0 + half * CTA_N;
-        if (row < m) store_row<CTA_N>(C + row + (long long)col0 * ldc, ldc, sum, n - col0, alpha, beta);
+        if (tma_c)
+          store_rows_tma<CTA_N>(&map_c, rg.staging(warp - 4), lane, m0 + (int)rank * CTA_M + q * 32, col0, m, n, sum, alpha);
+        else if (row < m)
+          store_row<CTA_N>(C + row + (long long)col0 * ldc, ldc, sum, n - col0, alpha, beta);
         continue;
       }
       // ---- stream-K partial: slot layout [column][row] of the whole 256 x 256 tile
@@ -793,6 +837,7 @@ sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
         }
       }
     }
+    if (tma_c && lane == 0) bulk_wait_read<0>();  // the staging buffers outlive their last bulk store
   }
 
   tc_fence_before();
@@ -818,6 +863,9 @@ struct MapSet {
   int device = -1, m = -1, n = -1, k = -1, lda = -1, ldb = -1;
   bool fused = false;
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
+  const void* pc = nullptr;  // what `c` describes (the TMA-store epilogue), nullptr: not encoded
+  int ldc = -1;
+  CUtensorMap c;
 };
 constexpr int kMapSets = 8;
 
@@ -888,8 +936,8 @@ int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const flo
       pairs_min = std::min(pairs_min, clusters);
       return 0;
     };
-    if (setup(pair::sgemm_3xtf32_pair_kernel<false>, Rings<false>::SMEM)) return 1;
-    if (setup(pair::sgemm_3xtf32_pair_kernel<true>, Rings<true>::SMEM)) return 1;
+    if (setup(pair::sgemm_3xtf32_pair_kernel<false>, Rings<false>::smem_bytes(pair::EPI_WARPS))) return 1;
+    if (setup(pair::sgemm_3xtf32_pair_kernel<true>, Rings<true>::smem_bytes(pair::EPI_WARPS))) return 1;
     g_pair_max_clusters = pairs_min;
     g_pair_attr_done = true;
   }
@@ -961,6 +1009,7 @@ int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const flo
     mc = &sets[next_set];
     next_set = (next_set + 1) % kMapSets;
     mc->pa = nullptr;
+    mc->pc = nullptr;
     if (make_tensor_map_2d(&mc->a_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, pa, m, k, (uint64_t)lda * 4, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 2;
     if (make_tensor_map_2d(&mc->b_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, pb, k, n, (uint64_t)ldb * 4, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B)) return 2;
     if (fused) {
@@ -974,6 +1023,15 @@ int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const flo
     mc->m = m; mc->n = n; mc->k = k; mc->lda = lda; mc->ldb = ldb;
   }
   const CUtensorMap &ma_hi = mc->a_hi, &ma_lo = mc->a_lo, &mb_hi = mc->b_hi, &mb_lo = mc->b_lo;
+  // TMA-store epilogue: whole tiles of a beta == 0 call whose C obeys TMA's alignment rules
+  // (the harness' case); everything else stores from registers
+  const int tma_c = ctx->opt_sgemm_tma_store && beta == 0.0f && (ldc % 4 == 0) && ((uintptr_t)C % 16 == 0);
+  if (tma_c && (mc->pc != C || mc->ldc != ldc)) {
+    mc->pc = nullptr;
+    if (make_tensor_map_2d(&mc->c, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, C, m, n, (uint64_t)ldc * 4, 32, 16, CU_TENSOR_MAP_SWIZZLE_NONE)) return 2;
+    mc->pc = C;
+    mc->ldc = ldc;
+  }
 
   if (!fused) {
     const int split_blocks = ctx->sm_count * 8;
@@ -984,16 +1042,20 @@ int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const flo
   }
 
   if (use_pair) {
+    // Raster: groups of 8 m-tiles walk along n, so the ~74 tiles in flight share A and B panels in
+    // L2.  With a short K there is nothing to share and the kernel is bound by the C writes: then
+    // whole columns of tiles (all m-tiles of an n-tile first) keep the rows being written
+    // contiguous in DRAM (M = N = 8192, K = 32: 58.1 -> 51.0 us; at K = 8192 the same order costs 3 %).
     static const char* rg_env = getenv("B200_SGEMM_RASTER");  // tuning: m-tiles per raster group
-    const int raster_group = rg_env ? std::max(1, atoi(rg_env)) : 8;
+    const int raster_group = rg_env ? std::max(1, atoi(rg_env)) : (k <= 256 ? std::max(8, (int)t2m) : 8);
     const int grid = 2 * (int)(sk_tiles ? pairs : std::min<long long>(tiles2, pairs));
     if (fused)
-      pair::sgemm_3xtf32_pair_kernel<true><<<grid, pair::THREADS, Rings<true>::SMEM, ctx->compute>>>(
-          ma_hi, ma_lo, mb_hi, mb_lo, m, n, k, alpha, beta, C, (long long)ldc, (int)t2m, (int)t2n, raster_group,
+      pair::sgemm_3xtf32_pair_kernel<true><<<grid, pair::THREADS, Rings<true>::smem_bytes(pair::EPI_WARPS), ctx->compute>>>(
+          ma_hi, ma_lo, mb_hi, mb_lo, mc->c, tma_c, m, n, k, alpha, beta, C, (long long)ldc, (int)t2m, (int)t2n, raster_group,
           sk_tiles, sk_slots, sk_partial, ctx->counters);
     else
-      pair::sgemm_3xtf32_pair_kernel<false><<<grid, pair::THREADS, Rings<false>::SMEM, ctx->compute>>>(
-          ma_hi, ma_lo, mb_hi, mb_lo, m, n, k, alpha, beta, C, (long long)ldc, (int)t2m, (int)t2n, raster_group,
+      pair::sgemm_3xtf32_pair_kernel<false><<<grid, pair::THREADS, Rings<false>::smem_bytes(pair::EPI_WARPS), ctx->compute>>>(
+          ma_hi, ma_lo, mb_hi, mb_lo, mc->c, tma_c, m, n, k, alpha, beta, C, (long long)ldc, (int)t2m, (int)t2n, raster_group,
           sk_tiles, sk_slots, sk_partial, ctx->counters);
     B200_CUDA(cudaGetLastError());
     if (fused)
@@ -1005,20 +1067,20 @@ int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const flo
   std::atomic<bool>& g_attr_done = g_attr_done_dev[ctx->device % kMaxDevices];
   if (!g_attr_done) {
     B200_CUDA(cudaFuncSetAttribute(sgemm_3xtf32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)Rings<false>::SMEM));
+                                   (int)Rings<false>::smem_bytes(SINGLE_EPI_WARPS)));
     B200_CUDA(cudaFuncSetAttribute(sgemm_3xtf32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)Rings<true>::SMEM));
+                                   (int)Rings<true>::smem_bytes(SINGLE_EPI_WARPS)));
     g_attr_done = true;
   }
   float* partial = splits > 1 ? (float*)(ws + need) : nullptr;
   const int grid = (int)std::min<long long>(tiles1 * splits, ctx->sm_count);
   if (fused)
-    sgemm_3xtf32_kernel<true><<<grid, NUM_THREADS, Rings<true>::SMEM, ctx->compute>>>(
-        ma_hi, ma_lo, mb_hi, mb_lo, m, n, k, alpha, beta, C, (long long)ldc, (int)t1m, (int)t1n, splits,
+    sgemm_3xtf32_kernel<true><<<grid, NUM_THREADS, Rings<true>::smem_bytes(SINGLE_EPI_WARPS), ctx->compute>>>(
+        ma_hi, ma_lo, mb_hi, mb_lo, mc->c, tma_c, m, n, k, alpha, beta, C, (long long)ldc, (int)t1m, (int)t1n, splits,
         kb_per_split, partial, ctx->counters);
   else
-    sgemm_3xtf32_kernel<false><<<grid, NUM_THREADS, Rings<false>::SMEM, ctx->compute>>>(
-        ma_hi, ma_lo, mb_hi, mb_lo, m, n, k, alpha, beta, C, (long long)ldc, (int)t1m, (int)t1n, splits,
+    sgemm_3xtf32_kernel<false><<<grid, NUM_THREADS, Rings<false>::smem_bytes(SINGLE_EPI_WARPS), ctx->compute>>>(
+        ma_hi, ma_lo, mb_hi, mb_lo, mc->c, tma_c, m, n, k, alpha, beta, C, (long long)ldc, (int)t1m, (int)t1n, splits,
         kb_per_split, partial, ctx->counters);
   B200_CUDA(cudaGetLastError());
   if (fused)

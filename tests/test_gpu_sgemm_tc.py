@@ -192,3 +192,31 @@ def test_sgemm_split_k_alpha_beta(blob, ctx, oracle):
     g, w = got.reshape(n, ldc), want.reshape(n, ldc)
     assert np.array_equal(g[:, m:], C0.reshape(n, ldc)[:, m:])  # padding rows untouched
     assert max_rel_err(g[:, :m].ravel(), w[:, :m].ravel()) <= 1e-5
+
+
+@pytest.mark.parametrize("pair", ["on", "off"])
+@pytest.mark.parametrize("shape", [(516, 772, 264), (1028, 260, 72), (2048, 2048, 32), (300, 2304, 72)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_sgemm_tma_store_epilogue_matches_register_stores(blob, ctx, oracle, shape, pair):
+    """beta == 0 with an aligned C goes through shared memory and cp.async.bulk.tensor stores
+    (clipped at the ragged edges by the tensor map); the register-store epilogue must give the
+    same bits, and rows / columns outside C must stay untouched."""
+    m, n, k = shape
+    if pair == "on" and (m < 256 or n < 256):
+        pytest.skip("pair tiles need m, n >= 256")
+    A, B, _ = oracle.init_gemm("f32", m, n, k)
+    ldc = m + 4  # 16-byte aligned, with padding rows the stores must not touch
+    C0 = np.full(ldc * n, -7.0, np.float32)
+    ctx.set_option("sgemm_pair", pair)
+    try:
+        got_tma, kern = run_gemm(blob, ctx, "f32", "once", m, n, k, A, B, C0=C0, ldc=ldc)
+        ctx.set_option("sgemm_tma_store", "off")
+        got_reg, kern2 = run_gemm(blob, ctx, "f32", "once", m, n, k, A, B, C0=C0, ldc=ldc)
+    finally:
+        ctx.set_option("sgemm_tma_store", "on")
+        ctx.set_option("sgemm_pair", "auto")
+    assert "tcgen05" in kern and kern == kern2, (kern, kern2)
+    assert np.array_equal(got_tma, got_reg)
+    assert np.all(got_tma.reshape(n, ldc)[:, m:] == -7.0)
+    want = oracle.harness_gemm("f32", m, n, k)
+    assert max_rel_err(got_tma.reshape(n, ldc)[:, :m].ravel(), want) <= 1e-5
