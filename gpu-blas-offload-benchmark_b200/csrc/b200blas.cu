@@ -370,6 +370,12 @@ int b200_ctx_set_option(b200_ctx* ctx, const char* key, const char* value) {
     else B200_REQUIRE(false, "b200_ctx_set_option: sgemm_tma_store must be on|off, got '%s'", value);
     return 0;
   }
+  if (!strcmp(key, "dgemm_smem_pad")) {
+    if (!strcmp(value, "on")) ctx->opt_dgemm_smem_pad = 1;
+    else if (!strcmp(value, "off") || !strcmp(value, "auto")) ctx->opt_dgemm_smem_pad = 0;
+    else B200_REQUIRE(false, "b200_ctx_set_option: dgemm_smem_pad must be on|off, got '%s'", value);
+    return 0;
+  }
   if (!strcmp(key, "tallk")) {
     if (!strcmp(value, "on") || !strcmp(value, "auto")) ctx->opt_tallk = 1;
     else if (!strcmp(value, "off")) ctx->opt_tallk = 0;

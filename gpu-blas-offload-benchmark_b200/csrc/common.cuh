@@ -85,6 +85,7 @@ struct b200_ctx {
   int opt_tallk = 1;       // M, N <= 32 with K >= 1024: the cluster / DSMEM split-K kernel (gemm_tallk.cu); 0 = the generic split-K paths
   int opt_dgemm_min = 32;  // smallest m, n the DMMA kernels take (one 32x32 tile; below: DFMA SIMT path)
   int opt_dgemm_streamk = 1;  // 1: stream-K over the partial last wave of the TMA kernel, 0: whole tiles only
+  int opt_dgemm_smem_pad = 0;  // test knob: launch the TMA DGEMM kernel with the maximum shared-memory carve-out (minimum L1)
   int opt_dgemm_tma = 1;   // 1: large aligned DGEMMs use the TMA-fed kernel, 0: cp.async kernel
   // Always mode: 1 = upload C / y even when beta == 0, as the reference does
   // (cuBLAS/gemm.hh:130-131, cuBLAS/gemv.hh:126-127); 0 = skip the dead upload.  B200_UPLOAD_C.

@@ -60,6 +60,10 @@ constexpr uint32_t A_STAGE_BYTES = (BM / 16) * BK * 128;  // 8 chunks x [32 k][1
 constexpr uint32_t B_STAGE_BYTES = (BK / 16) * BN * 128;  // 2 halves x [128 n][128 B]
 constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 64;
+// "dgemm_smem_pad": launch with (nearly) all of the SM's shared memory, which leaves the L1 its
+// minimum size -- the configuration in which the stage-release race described in run_tile showed
+// up within a few launches (tests/test_gpu_dgemm_streamk.py keeps it covered)
+constexpr uint32_t SMEM_BYTES_PADDED = 226 * 1024;
 constexpr int MI = 8, NI = 4;  // DMMA tiles per warp (64 x 32 warp tile)
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
@@ -83,7 +87,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 dgemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  int m, int n, int k, double alpha, double beta, double* __restrict__ C, long long ldc,
                  int tiles_m, int tiles_n, int k_per_split, double* __restrict__ partial,
-                 unsigned int* __restrict__ counters, int sk_tiles, int sk_slots) {
+                 unsigned int* __restrict__ counters, int sk_tiles, int sk_slots, unsigned int zero) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = base + STAGES * STAGE_BYTES;
@@ -253,8 +257,24 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           for (int ni = 0; ni < NI; ni++)
             dmma(acc[mi][ni][0], acc[mi][ni][1], a[cur][mi], s ? b2[kk & 1][ni].y : b2[kk & 1][ni].x);
       }
+      // Releasing the stage lets the producer's next TMA overwrite it, so every fragment load
+      // must have RETURNED by then.  Shared-memory loads are asynchronous (a register is only
+      // waited for by the instruction that reads it) and DMMA is register-only, so ptxas is free
+      // to move the mbarrier arrive up between the last loads' issue and the DMMAs that consume
+      // them -- it did: LDS, LDS, SYNCS.ARRIVE, DMMA in the SASS -- and when the LSU queue is
+      // backed up (beta != 0 epilogues of the other warps streaming C through a minimum-size L1)
+      // a load could still be in flight when the refill landed: one DMMA step of a warp computed
+      // on the k-tile three ahead (errors of a few products in C(+)= blocks, found by the
+      // Always-mode pipeline test once the kernel asked for more shared memory).  Tie the barrier
+      // address to one word of every load result: `zero` is a kernel argument, always 0, that the
+      // compiler cannot fold, so the arrive cannot issue before the loads have completed.
+      uint32_t dep = 0;
+#pragma unroll
+      for (int mi = 0; mi < MI; mi++) dep ^= (uint32_t)__double2loint(a[0][mi]) ^ (uint32_t)__double2loint(a[1][mi]);
+#pragma unroll
+      for (int ni = 0; ni < NI; ni++) dep ^= (uint32_t)__double2loint(b2[0][ni].x) ^ (uint32_t)__double2loint(b2[1][ni].x);
       __syncwarp();
-      if (lane == 0) mbar_arrive(empty_bar(stage));
+      if (lane == 0) mbar_arrive(empty_bar(stage) + dep * zero);
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
   };
@@ -490,14 +510,14 @@ int dgemm_tma_dispatch(b200_ctx* ctx, int m, int n, int k, double alpha, const d
     return 2;
   std::atomic<bool>& g_attr_done = g_attr_done_dev[ctx->device % kMaxDevices];
   if (!g_attr_done) {
-    B200_CUDA(cudaFuncSetAttribute(dgemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    B200_CUDA(cudaFuncSetAttribute(dgemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_PADDED));
     g_attr_done = true;
   }
   // no split-K: persistent CTAs, one per SM, each walks tiles b, b + grid, ...
   dim3 grid((unsigned)(splits > 1 ? tiles : (sk_tiles ? P : std::min<long long>(tiles, P))), splits);
-  dgemm_tma_kernel<<<grid, NTHREADS, SMEM_BYTES, ctx->compute>>>(map_a, map_b, m, n, k, alpha, beta, C,
-                                                                 (long long)ldc, tiles_m, tiles_n, k_per_split,
-                                                                 partial, ctx->counters, sk_tiles, sk_slots);
+  dgemm_tma_kernel<<<grid, NTHREADS, ctx->opt_dgemm_smem_pad ? SMEM_BYTES_PADDED : SMEM_BYTES, ctx->compute>>>(
+      map_a, map_b, m, n, k, alpha, beta, C, (long long)ldc, tiles_m, tiles_n, k_per_split, partial, ctx->counters,
+      sk_tiles, sk_slots, 0u);
   B200_CUDA(cudaGetLastError());
   note_launch(ctx, splits > 1 ? "dgemm_dmma_tma_128x128x32_splitk"
                           : (sk_tiles ? "dgemm_dmma_tma_128x128x32_streamk" : "dgemm_dmma_tma_128x128x32"));

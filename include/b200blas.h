@@ -51,7 +51,9 @@ enum { B200_OP_N = 0, B200_OP_T = 1 };
  * cudaStreamCreate (cuBLAS/gemm.hh:46-63, cuBLAS/gemv.hh:46-60) and
  * cublasDestroy + 3x cudaStreamDestroy (cuBLAS/gemm.hh:26-36).
  * `device` < 0 selects the current CUDA device.  Contexts are independent:
- * the harness keeps up to four backend objects alive (src/main.cc:35-59). */
+ * the harness keeps up to four backend objects alive (src/main.cc:35-59).
+ * Every call that takes a context runs on that context's device whatever device is
+ * current in the calling thread, and leaves the thread's current device as it found it. */
 int b200_ctx_create(b200_ctx** out, int device);
 int b200_ctx_destroy(b200_ctx* ctx);
 /* Use a caller-owned stream (e.g. the torch current stream) as the compute
@@ -65,8 +67,18 @@ int b200_ctx_device(const b200_ctx* ctx, int* device, int* sm_count);
  *   "dgemm_streamk" = "on" | "off" (TMA kernel: stream-K over the partial last wave of tiles)
  *   "sgemm_streamk" = "on" | "off" (CTA-pair SGEMM kernel: stream-K over the partial last wave of tiles)
  *   "sgemm_pair" = "auto" | "on" | "off" (tcgen05 SGEMM: CTA-pair 256x256 tiles vs single-CTA 128x128)
- * Defaults come from the environment at context creation: B200_SGEMM, B200_SGEMM_PAIR,
- * B200_DGEMM_TILE, B200_DGEMM_TMA, B200_DGEMM_STREAMK, B200_UPLOAD_C.
+ *   "sgemm_fused" = "auto" | "on" | "off" (3xTF32 operand split: fused into the GEMM -- TMA lands the raw
+ *                  FP32 tiles, converter warps write the lo parts -- vs a separate pre-pass that writes
+ *                  hi/lo copies of A and B into the workspace)
+ *   "sgemm_tma_store" = "on" | "off" (tcgen05 SGEMM, beta == 0, 16-byte aligned C: tiles leave through
+ *                  shared memory and cp.async.bulk.tensor stores vs register stores)
+ *   "dgemm_smem_pad" = "off" | "on" (test knob: launch the TMA DGEMM kernel with the maximum shared-memory
+ *                  carve-out, i.e. the minimum L1 -- the setting that exposes stage-release races)
+ *   "tallk"      = "on" | "off"   (m, n <= 32 and k >= 1024: the cluster / distributed-shared-memory
+ *                  split-K kernel vs the generic split-K paths)
+ * Defaults come from the environment at context creation: B200_SGEMM, B200_SGEMM_PAIR, B200_SGEMM_FUSED,
+ * B200_SGEMM_TMA_STORE, B200_TALLK, B200_DGEMM_TILE, B200_DGEMM_TMA,
+ * B200_DGEMM_STREAMK, B200_UPLOAD_C.
  *   "upload_c"   = "off" | "on"  (Always mode: upload C / y even when beta == 0, as the reference
  *                  does at cuBLAS/gemm.hh:130-131 and cuBLAS/gemv.hh:126-127; default off -- BLAS
  *                  never reads the output operand when beta == 0)

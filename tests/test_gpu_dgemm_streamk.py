@@ -84,3 +84,38 @@ def test_dgemm_tma_alpha_beta(blob, ctx, oracle, shape, expect):
         oracle.gemm("f64", bs, bs, k, 1.5, a_cm, bs, b_cm, k, -0.25, want, bs)
         got = np.ascontiguousarray(Ch[j0:j0 + bs, i0:i0 + bs]).reshape(-1)
         assert max_rel_err(got, want) <= 1e-12, (shape, kern, (i0, j0))
+
+
+@pytest.mark.parametrize("pad", ["off", "on"])
+@pytest.mark.parametrize("shape", [(4096, 4096, 1024), (6144, 1024, 1024), (4096, 4096, 96)], ids=lambda s: "x".join(map(str, s)))
+def test_dgemm_accumulate_blocks_are_exact(blob, ctx, shape, pad):
+    """C += A * B (beta = 1: the accumulate blocks of the Always-mode pipeline and of the multi-GPU
+    K-chunk loop) must equal C_old + (A * B by the beta = 0 call) to the last bit -- the update
+    is one FMA per element -- on every repetition.  Regression for a stage-release race in the TMA
+    pipeline: the mbarrier arrive that frees a stage could issue while the last fragment loads of
+    that stage were still in flight; with the LSU queue backed up by the beta != 0 epilogue a
+    refill overtook them and single DMMA steps ran on the wrong k-tile.  "dgemm_smem_pad" = on
+    launches with the maximum shared-memory carve-out (minimum L1), where the unfixed kernel
+    failed within a few launches."""
+    import torch
+    m, n, k = shape
+    A = _fill(torch, m * k, 51, 7.0)
+    B = _fill(torch, k * n, 52, 3.0)
+    Cold = _fill(torch, m * n, 53, 0.001)
+    P = torch.zeros(m * n, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    ctx.set_option("dgemm_smem_pad", pad)
+    try:
+        ctx.gemm("f64", m, n, k, 1.0, A, m, B, k, 0.0, P, m)
+        ctx.sync()
+        assert ctx.last_kernel().startswith("dgemm_dmma_tma"), ctx.last_kernel()
+        want = Cold + P
+        for rep in range(6):
+            C = Cold.clone()
+            torch.cuda.synchronize()
+            ctx.gemm("f64", m, n, k, 1.0, A, m, B, k, 1.0, C, m)
+            ctx.sync()
+            bad = int((C != want).sum().item())
+            assert bad == 0, (shape, pad, rep, bad)
+    finally:
+        ctx.set_option("dgemm_smem_pad", "off")

@@ -1,0 +1,67 @@
+"""Perf guard for Unified mode (reference choreography cuBLAS/gemm.hh:108-116,
+174-189,210-216: prefetch the managed operands to the GPU, ten kernels, prefetch C back).
+
+Round 1's harness tables had order-of-magnitude Unified outliers (SGEMM 8192^3 at 11 TFLOP/s
+against 219 in Once mode).  The timed region here is the harness' own (preLoop + 10 calls +
+postLoop, host clock); the MEDIAN of five repetitions must stay within 2x of Once mode -- rare
+UVM-driver stalls of a single repetition (profiles/r1_unified_notes.md) do not move a median,
+a systematic collapse does."""
+import time
+
+import numpy as np
+import pytest
+
+from test_gpu_parity import MODES, Operand
+
+pytestmark = pytest.mark.gpu
+
+
+def timed_compute(blob, ctx, dt, mode, d, iters=10):
+    md = MODES[mode]
+    ops = [Operand(blob, ctx, md, dt, d * d) for _ in range(3)]
+    a, b, c = ops
+    try:
+        rng = np.random.default_rng(5)
+        a.np[:] = (rng.integers(0, 100, d * d) / 7.0).astype(a.np.dtype)
+        b.np[:] = (rng.integers(0, 100, d * d) / 3.0).astype(b.np.dtype)
+        c.np[:] = 0
+        if mode == "unified":
+            for o, inp in ((a, 1), (b, 1), (c, 0)):
+                ctx.advise(o.dev, o.nbytes, inp)
+        if dt == "f32":
+            ctx.sgemm_prepare(d, d, d, d, d)
+        times = []
+        for _ in range(6):
+            ctx.sync()
+            t0 = time.perf_counter()
+            if mode == "once":
+                ctx.h2d(a.dev, a.host, a.nbytes, 0)
+                ctx.h2d(b.dev, b.host, b.nbytes, 1)
+            else:
+                ctx.prefetch(a.dev, a.nbytes, True, 0)
+                ctx.prefetch(b.dev, b.nbytes, True, 1)
+                ctx.prefetch(c.dev, c.nbytes, True, 2)
+            for _ in range(iters):
+                ctx.gemm(dt, d, d, d, 1.0, a.dev, d, b.dev, d, 0.0, c.dev, d)
+            if mode == "once":
+                ctx.d2h(c.host, c.dev, c.nbytes, 2)
+            else:
+                ctx.prefetch(c.dev, c.nbytes, False, 2)
+            ctx.sync()
+            times.append(time.perf_counter() - t0)
+            _ = float(c.np[0]) + float(c.np[-1])  # the host reads the result, as calcChecksum does
+        return float(np.median(times[1:])), ctx.last_kernel()
+    finally:
+        for o in ops:
+            o.free()
+
+
+@pytest.mark.parametrize("d", [4096, 8192])
+@pytest.mark.parametrize("dt", ["f64", "f32"])
+def test_unified_mode_within_2x_of_once(blob, ctx, dt, d):
+    once, kern = timed_compute(blob, ctx, dt, "once", d)
+    unified, kern_u = timed_compute(blob, ctx, dt, "unified", d)
+    flops = 10 * (2.0 * d ** 3 + d * d)
+    print(f"{dt} {d}^3: once {flops / once * 1e-12:.1f} TFLOP/s, unified {flops / unified * 1e-12:.1f} TFLOP/s ({kern_u})")
+    assert kern == kern_u
+    assert unified <= 2.0 * once, (dt, d, once, unified)
