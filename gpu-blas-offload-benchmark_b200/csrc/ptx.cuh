@@ -59,6 +59,18 @@ __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// One lane of a CONVERGED warp (always the same one for the same mask).  The single-thread
+// instructions (TMA issue, tcgen05.mma, tcgen05.commit) are put under `if (elect_one())` INSIDE
+// warp-uniform loops: a role loop that runs entirely under `if (lane == 0)` is divergent code,
+// where the uniform datapath cannot be used, and every UTMALDG / UTCHMMA then pays an
+// ELECT + 5 x R2UR + branch sequence to get its descriptors into uniform registers (~25
+// instructions per MMA from one warp: the 64-clock UMMAs of the single-CTA SGEMM kernel were
+// issue-bound on it).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t slot, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(cols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");

@@ -49,6 +49,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <vector>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -217,6 +218,18 @@ __device__ __forceinline__ void convert_slot(uint32_t src, uint32_t dst, int t) 
   }
 }
 
+// B200_SGEMM_TRACE: per-CTA timestamps (globaltimer, ns) at the phase boundaries of a launch,
+// summarised by the host after the launch (diagnostic; `trace` is nullptr otherwise).
+//   0 entry  1 set-up done  2 first operands ready (MMA warp)  3 last MMA issued
+//   4 last accumulator chunk ready (epilogue warp 4)  5 that warp's stores issued  6 exit
+__device__ __forceinline__ void trace_mark(unsigned long long* trace, int slot) {
+  if (trace) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    trace[(size_t)blockIdx.x * 8 + slot] = t;
+  }
+}
+
 // Store one thread's row of `NCOL` column results: C[row, col0 + j] = alpha * sum[j] (+ beta * C).
 // The per-column work is kept to a multiply, an address step and the store: guards and the
 // beta test are hoisted (ncu on M = N = 8192, K = 32: the epilogue warps were issue-latency
@@ -279,7 +292,7 @@ sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                     const __grid_constant__ CUtensorMap map_c, int tma_c,
                     int m, int n, int k, float alpha, float beta, float* __restrict__ C, long long ldc,
                     int tiles_m, int tiles_n, int splits, int kb_per_split, float* __restrict__ partial,
-                    unsigned int* __restrict__ counters) {
+                    unsigned int* __restrict__ counters, unsigned long long* __restrict__ trace) {
   using RG = Rings<FUSED>;
   constexpr int R = RG::R, L = RG::L;
   extern __shared__ uint8_t smem_raw[];
@@ -298,6 +311,7 @@ sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
   };
 
   if (threadIdx.x == 0) {
+    trace_mark(trace, 0);
     for (int s = 0; s < R; s++) {
       mbar_init(rg.hi_full(s), 1);
       mbar_init(rg.hi_empty(s), 1);
@@ -317,6 +331,7 @@ sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  if (threadIdx.x == 0) trace_mark(trace, 1);
 
   auto tile_coords = [&](int tile, int& m0, int& n0) {
     constexpr int GROUP = 8;
@@ -328,16 +343,17 @@ sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
   };
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      Pos r;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        int m0, n0, kb_lo, kb_hi;
-        tile_coords(item / splits, m0, n0);
-        kb_range(item, kb_lo, kb_hi);
-        for (int kb = kb_lo; kb < kb_hi; kb++) {
-          mbar_wait(rg.hi_empty(r.i), r.ph ^ 1);
-          const uint32_t bar = rg.hi_full(r.i);
+    // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
+    const bool elected = elect_one();
+    Pos r;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      int m0, n0, kb_lo, kb_hi;
+      tile_coords(item / splits, m0, n0);
+      kb_range(item, kb_lo, kb_hi);
+      for (int kb = kb_lo; kb < kb_hi; kb++) {
+        mbar_wait(rg.hi_empty(r.i), r.ph ^ 1);
+        const uint32_t bar = rg.hi_full(r.i);
+        if (elected) {
           mbar_expect_tx(bar, FUSED ? SLOT : 2 * SLOT);
 #pragma unroll
           for (int c = 0; c < BM / 32; c++) tma_load_2d(rg.a_hi(r.i) + c * 4096, &map_a_hi, bar, m0 + c * 32, kb * BK);
@@ -347,8 +363,9 @@ sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
             for (int c = 0; c < BM / 32; c++) tma_load_2d(rg.a_lo(r.i) + c * 4096, &map_a_lo, bar, m0 + c * 32, kb * BK);
             tma_load_2d(rg.b_lo(r.i), &map_b_lo, bar, kb * BK, n0);
           }
-          r.next<R>();
         }
+        __syncwarp();
+        r.next<R>();
       }
     }
   } else if (warp == 1) {
@@ -358,7 +375,11 @@ sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     // TMEM only ever accumulates KB_PER_CHUNK k-blocks; the epilogue warps promote
     // each chunk into round-to-nearest FP32 registers while the next chunk runs in
     // the other accumulator stage.
-    if (lane == 0) {
+    // The loop is warp-uniform (all lanes wait on the barriers and carry the ring positions, so
+    // the descriptors live in uniform registers); one elected lane issues the MMAs and commits.
+    {
+      const bool elected = elect_one();
+      bool first_kb = true;
       Pos r, l, acc;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         int kb_lo, kb_hi;
@@ -372,29 +393,36 @@ sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
             mbar_wait(rg.hi_full(r.i), r.ph);  // the TMA writes (FUSED: the converters saw them too)
             if (FUSED) mbar_wait(rg.lo_full(l.i), l.ph);
             tc_fence_after();
+            if (first_kb) {
+              if (elected) trace_mark(trace, 2);
+              first_kb = false;
+            }
             const int li = FUSED ? l.i : r.i;
             const uint32_t sa_hi = rg.a_hi(r.i), sb_hi = rg.b_hi(r.i), sa_lo = rg.a_lo(li), sb_lo = rg.b_lo(li);
+            if (elected) {
 #pragma unroll
-            for (int ks = 0; ks < BK / UMMA_K; ks++) {
-              const uint64_t a_hi = umma_desc(sa_hi + ks * 1024, 4096, 512, kSwizzle128B_Base32B);
-              const uint64_t a_lo = umma_desc(sa_lo + ks * 1024, 4096, 512, kSwizzle128B_Base32B);
-              const uint64_t b_hi = umma_desc(sb_hi + ks * 32, 16, 1024, kSwizzle128B);
-              const uint64_t b_lo = umma_desc(sb_lo + ks * 32, 16, 1024, kSwizzle128B);
-              umma_tf32(d_tmem, a_lo, b_hi, kIdesc, (kb != kb0) || (ks != 0));
-              umma_tf32(d_tmem, a_hi, b_lo, kIdesc, 1);
-              umma_tf32(d_tmem, a_hi, b_hi, kIdesc, 1);
+              for (int ks = 0; ks < BK / UMMA_K; ks++) {
+                const uint64_t a_hi = umma_desc(sa_hi + ks * 1024, 4096, 512, kSwizzle128B_Base32B);
+                const uint64_t a_lo = umma_desc(sa_lo + ks * 1024, 4096, 512, kSwizzle128B_Base32B);
+                const uint64_t b_hi = umma_desc(sb_hi + ks * 32, 16, 1024, kSwizzle128B);
+                const uint64_t b_lo = umma_desc(sb_lo + ks * 32, 16, 1024, kSwizzle128B);
+                umma_tf32(d_tmem, a_lo, b_hi, kIdesc, (kb != kb0) || (ks != 0));
+                umma_tf32(d_tmem, a_hi, b_lo, kIdesc, 1);
+                umma_tf32(d_tmem, a_hi, b_hi, kIdesc, 1);
+              }
+              umma_commit(rg.hi_empty(r.i));  // frees the slot(s) when these MMAs finish
+              if (FUSED) umma_commit(rg.lo_empty(l.i));
             }
-            umma_commit(rg.hi_empty(r.i));  // frees the slot(s) when these MMAs finish
-            if (FUSED) {
-              umma_commit(rg.lo_empty(l.i));
-              l.next<L>();
-            }
+            __syncwarp();
+            if (FUSED) l.next<L>();
             r.next<R>();
           }
-          umma_commit(rg.tfull(acc.i));  // chunk complete -> epilogue promotes it
+          if (elected) umma_commit(rg.tfull(acc.i));  // chunk complete -> epilogue promotes it
+          __syncwarp();
           acc.next<ACC_STAGES>();
         }
       }
+      if (elected) trace_mark(trace, 3);
     }
   } else if (warp < 4) {
     // ===================== converters (FUSED): lo ring <- hi ring =====================
@@ -432,6 +460,7 @@ sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
       for (int kb0 = kb_lo; kb0 < kb_hi; kb0 += KB_PER_CHUNK) {
         mbar_wait(rg.tfull(acc.i), acc.ph);
         tc_fence_after();
+        if (threadIdx.x == 128) trace_mark(trace, 4);
         const uint32_t taddr = tmem_base + acc.i * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll
         for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -502,12 +531,14 @@ sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
           if (row0 + e < m) cp[e] = (beta == 0.0f) ? alpha * rr[e] : alpha * rr[e] + beta * cp[e];
       }
     }
+    if (threadIdx.x == 128) trace_mark(trace, 5);
     if (tma_c && lane == 0) bulk_wait_read<0>();  // the staging buffers outlive their last bulk store
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (threadIdx.x == 0) trace_mark(trace, 6);
 }
 
 // ------------------------------------------------- CTA-pair kernel (256 x 256)
@@ -552,7 +583,8 @@ sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
                          const __grid_constant__ CUtensorMap map_c, int tma_c,
                          int m, int n, int k, float alpha, float beta, float* __restrict__ C, long long ldc,
                          int tiles_m, int tiles_n, int raster_group, int sk_tiles, int sk_slots,
-                         float* __restrict__ partial, unsigned int* __restrict__ counters) {
+                         float* __restrict__ partial, unsigned int* __restrict__ counters,
+                         unsigned long long* __restrict__ trace) {
   using RG = Rings<FUSED>;
   constexpr int R = RG::R, L = RG::L;
   extern __shared__ uint8_t smem_raw[];
@@ -573,8 +605,8 @@ sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
   // then, if the tile count leaves a partial last wave, this pair's segment of the stream-K space:
   // the accumulation chunks (K = 128) of the last sk_tiles tiles, cut into num_pairs equal
   // contiguous runs (same scheme as the DGEMM kernel, csrc/dgemm_tma.cu).  A run that does not
-  // cover its whole tile publishes a partial tile; the last CTA to arrive for the tile adds the
-  // partials in contributor order and stores C.
+  // cover its whole tile publishes a partial tile; per half of the tile (the 128 rows of one CTA
+  // rank) the last CTA of that rank to arrive adds the partials in contributor order and stores C.
   const int chunks = (num_kb + KB_PER_CHUNK - 1) / KB_PER_CHUNK;
   const int dp_tiles = num_tiles - sk_tiles;
   const long long sk_units = (long long)sk_tiles * chunks;
@@ -605,6 +637,7 @@ sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
   };
 
   if (threadIdx.x == 0) {
+    trace_mark(trace, 0);
     for (int s = 0; s < R; s++) {
       mbar_init(rg.hi_full(s), 1);
       mbar_init(rg.hi_empty(s), 1);
@@ -625,6 +658,7 @@ sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
   cluster_sync();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  if (threadIdx.x == 0) trace_mark(trace, 1);
 
   auto tile_coords = [&](int tile, int& m0, int& n0) {
     const int GROUP = raster_group;
@@ -637,8 +671,9 @@ sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
 
   if (warp < 4) {
     setmaxnreg_dec<48>();
-    if (warp == 0 && lane == 0) {
-      // ===================== TMA producer (both CTAs) =====================
+    if (warp == 0) {
+      // ===================== TMA producer (both CTAs; warp-uniform loop, one elected lane issues) =====================
+      const bool elected = elect_one();
       Pos r, l;
       Item w;
       while (next_item(w)) {
@@ -650,22 +685,27 @@ sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
           mbar_wait(rg.hi_empty(r.i), r.ph ^ 1);
           if (FUSED) {
             const uint32_t bar = rg.hi_full(r.i);
-            mbar_expect_tx(bar, SLOT);
+            if (elected) {
+              mbar_expect_tx(bar, SLOT);
 #pragma unroll
-            for (int c = 0; c < CTA_M / 32; c++) tma_load_2d(rg.a_hi(r.i) + c * 4096, &map_a_hi, bar, my_m + c * 32, kb * BK);
-            tma_load_2d(rg.b_hi(r.i), &map_b_hi, bar, kb * BK, my_n);
+              for (int c = 0; c < CTA_M / 32; c++) tma_load_2d(rg.a_hi(r.i) + c * 4096, &map_a_hi, bar, my_m + c * 32, kb * BK);
+              tma_load_2d(rg.b_hi(r.i), &map_b_hi, bar, kb * BK, my_n);
+            }
             l.next<L>();
           } else {
-            if (rank == 0) mbar_expect_tx(rg.hi_full(r.i), 4 * SLOT);
             const uint32_t lbar = mapa_shared(rg.hi_full(r.i), 0);
+            if (elected) {
+              if (rank == 0) mbar_expect_tx(rg.hi_full(r.i), 4 * SLOT);
 #pragma unroll
-            for (int c = 0; c < CTA_M / 32; c++) {
-              tma_load_2d_2sm(rg.a_hi(r.i) + c * 4096, &map_a_hi, lbar, my_m + c * 32, kb * BK);
-              tma_load_2d_2sm(rg.a_lo(r.i) + c * 4096, &map_a_lo, lbar, my_m + c * 32, kb * BK);
+              for (int c = 0; c < CTA_M / 32; c++) {
+                tma_load_2d_2sm(rg.a_hi(r.i) + c * 4096, &map_a_hi, lbar, my_m + c * 32, kb * BK);
+                tma_load_2d_2sm(rg.a_lo(r.i) + c * 4096, &map_a_lo, lbar, my_m + c * 32, kb * BK);
+              }
+              tma_load_2d_2sm(rg.b_hi(r.i), &map_b_hi, lbar, kb * BK, my_n);
+              tma_load_2d_2sm(rg.b_lo(r.i), &map_b_lo, lbar, kb * BK, my_n);
             }
-            tma_load_2d_2sm(rg.b_hi(r.i), &map_b_hi, lbar, kb * BK, my_n);
-            tma_load_2d_2sm(rg.b_lo(r.i), &map_b_lo, lbar, kb * BK, my_n);
           }
+          __syncwarp();
           r.next<R>();
         }
       }
@@ -680,8 +720,10 @@ sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
           mbar_wait(rg.lo_empty(l.i), l.ph ^ 1);
           l.next<L>();
         }
-    } else if (warp == 1 && rank == 0 && lane == 0) {
-      // ===================== MMA issuer (leader CTA) =====================
+    } else if (warp == 1 && rank == 0) {
+      // ===================== MMA issuer (leader CTA; warp-uniform loop, one elected lane issues) =====================
+      const bool elected = elect_one();
+      bool first_kb = true;
       Pos r, l, acc;
       Item w;
       while (next_item(w)) {
@@ -695,29 +737,36 @@ sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
             mbar_wait(rg.hi_full(r.i), r.ph);  // FUSED: this CTA's raw tiles; the peer's are behind lo_full
             if (FUSED) mbar_wait(rg.lo_full(l.i), l.ph);
             tc_fence_after();
+            if (first_kb) {
+              if (elected) trace_mark(trace, 2);
+              first_kb = false;
+            }
             const int li = FUSED ? l.i : r.i;
             const uint32_t sa_hi = rg.a_hi(r.i), sb_hi = rg.b_hi(r.i), sa_lo = rg.a_lo(li), sb_lo = rg.b_lo(li);
+            if (elected) {
 #pragma unroll
-            for (int ks = 0; ks < BK / UMMA_K; ks++) {
-              const uint64_t a_hi = umma_desc(sa_hi + ks * 1024, 4096, 512, kSwizzle128B_Base32B);
-              const uint64_t a_lo = umma_desc(sa_lo + ks * 1024, 4096, 512, kSwizzle128B_Base32B);
-              const uint64_t b_hi = umma_desc(sb_hi + ks * 32, 16, 1024, kSwizzle128B);
-              const uint64_t b_lo = umma_desc(sb_lo + ks * 32, 16, 1024, kSwizzle128B);
-              umma_tf32_2sm(d_tmem, a_lo, b_hi, kIdesc2, (kb != kb0) || (ks != 0));
-              umma_tf32_2sm(d_tmem, a_hi, b_lo, kIdesc2, 1);
-              umma_tf32_2sm(d_tmem, a_hi, b_hi, kIdesc2, 1);
+              for (int ks = 0; ks < BK / UMMA_K; ks++) {
+                const uint64_t a_hi = umma_desc(sa_hi + ks * 1024, 4096, 512, kSwizzle128B_Base32B);
+                const uint64_t a_lo = umma_desc(sa_lo + ks * 1024, 4096, 512, kSwizzle128B_Base32B);
+                const uint64_t b_hi = umma_desc(sb_hi + ks * 32, 16, 1024, kSwizzle128B);
+                const uint64_t b_lo = umma_desc(sb_lo + ks * 32, 16, 1024, kSwizzle128B);
+                umma_tf32_2sm(d_tmem, a_lo, b_hi, kIdesc2, (kb != kb0) || (ks != 0));
+                umma_tf32_2sm(d_tmem, a_hi, b_lo, kIdesc2, 1);
+                umma_tf32_2sm(d_tmem, a_hi, b_hi, kIdesc2, 1);
+              }
+              umma_commit_2sm(rg.hi_empty(r.i), 3);  // frees the slot(s) in both CTAs
+              if (FUSED) umma_commit_2sm(rg.lo_empty(l.i), 3);
             }
-            umma_commit_2sm(rg.hi_empty(r.i), 3);  // frees the slot(s) in both CTAs
-            if (FUSED) {
-              umma_commit_2sm(rg.lo_empty(l.i), 3);
-              l.next<L>();
-            }
+            __syncwarp();
+            if (FUSED) l.next<L>();
             r.next<R>();
           }
-          umma_commit_2sm(rg.tfull(acc.i), 3);  // chunk complete -> both CTAs' epilogues
+          if (elected) umma_commit_2sm(rg.tfull(acc.i), 3);  // chunk complete -> both CTAs' epilogues
+          __syncwarp();
           acc.next<ACC_STAGES>();
         }
       }
+      if (elected) trace_mark(trace, 3);
     } else if (FUSED && warp >= 2) {
       // ===================== converters (both CTAs): lo ring <- hi ring =====================
       const int ct = threadIdx.x - 64;  // 0..63
@@ -761,6 +810,7 @@ sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
       for (int ch = w.c0; ch < w.c1; ch++) {
         mbar_wait(rg.tfull(acc.i), acc.ph);
         tc_fence_after();
+        if (threadIdx.x == 128) trace_mark(trace, 4);
         const uint32_t taddr = tmem_base + acc.i * PAIR_N + half * CTA_N + ((uint32_t)(q * 32) << 16);
 #pragma unroll
         for (int c0 = 0; c0 < CTA_N; c0 += 32) {
@@ -796,10 +846,14 @@ sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
       }
       __threadfence();
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      // Each CTA of the pair owns its 128 rows of the tile to the end: the rows of rank r are complete
+      // when the rank-r CTA of every contributing pair has published, and the last of THOSE adds
+      // them -- so the two halves of a tile are finished by two CTAs in parallel (one CTA reducing
+      // the whole 256 x 256 tile was the long pole of the fix-up: B200_SGEMM_TRACE, 4096^3, ~20 us).
       if (et == 0) {
-        const unsigned int prev = atomicAdd(&counters[t], 1u);
-        const int last = (prev == 2u * (unsigned)ncontrib - 1u);  // both CTAs of every contributing pair
-        if (last) counters[t] = 0;  // self-reset for the next launch
+        const unsigned int prev = atomicAdd(&counters[2 * t + (int)rank], 1u);
+        const int last = (prev == (unsigned)ncontrib - 1u);
+        if (last) counters[2 * t + (int)rank] = 0;  // self-reset for the next launch
         s_is_last = last;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -807,36 +861,34 @@ sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
       asm volatile("bar.sync 1, 256;" ::: "memory");  // flag read by all before it can be rewritten
       if (!last) continue;
       __threadfence();
-      // this CTA finishes the WHOLE tile (both halves): thread = 4 consecutive rows x 64 columns,
-      // two passes of 32 columns, 32 independent 16-byte loads in flight per contributor
-      const int rg4 = et & 63, cg = et >> 6;
-      const int row0 = m0 + rg4 * 4;
-#pragma unroll 1
-      for (int pass = 0; pass < 2; pass++) {
-        const int cbase = cg * 64 + pass * 32;
-        float4 tot[32];
+      // thread = 4 consecutive rows x 32 columns: 32 independent 16-byte loads in flight per contributor
+      const int rg4 = et & 31, cg = et >> 5;
+      const int hrow = (int)rank * CTA_M + rg4 * 4;  // row inside the tile
+      const int row0 = m0 + hrow;
+      const int cbase = cg * 32;
+      float4 tot[32];
 #pragma unroll
-        for (int j = 0; j < 32; j++) tot[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int z = 0; z < ncontrib; z++) {
-          const float* src = slots + (size_t)z * (PAIR_M * PAIR_N) + (size_t)cbase * PAIR_M + rg4 * 4;
-#pragma unroll
-          for (int j = 0; j < 32; j++) {
-            const float4 v = __ldcg(reinterpret_cast<const float4*>(src + j * PAIR_M));
-            tot[j].x += v.x; tot[j].y += v.y; tot[j].z += v.z; tot[j].w += v.w;
-          }
-        }
+      for (int j = 0; j < 32; j++) tot[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int z = 0; z < ncontrib; z++) {
+        const float* src = slots + (size_t)z * (PAIR_M * PAIR_N) + (size_t)cbase * PAIR_M + hrow;
 #pragma unroll
         for (int j = 0; j < 32; j++) {
-          const int col = n0 + cbase + j;
-          if (col >= n) continue;
-          float* cp = C + row0 + (long long)col * ldc;
-          const float rr[4] = {tot[j].x, tot[j].y, tot[j].z, tot[j].w};
-#pragma unroll
-          for (int e = 0; e < 4; e++)
-            if (row0 + e < m) cp[e] = (beta == 0.0f) ? alpha * rr[e] : alpha * rr[e] + beta * cp[e];
+          const float4 v = __ldcg(reinterpret_cast<const float4*>(src + j * PAIR_M));
+          tot[j].x += v.x; tot[j].y += v.y; tot[j].z += v.z; tot[j].w += v.w;
         }
       }
+#pragma unroll
+      for (int j = 0; j < 32; j++) {
+        const int col = n0 + cbase + j;
+        if (col >= n) continue;
+        float* cp = C + row0 + (long long)col * ldc;
+        const float rr[4] = {tot[j].x, tot[j].y, tot[j].z, tot[j].w};
+#pragma unroll
+        for (int e = 0; e < 4; e++)
+          if (row0 + e < m) cp[e] = (beta == 0.0f) ? alpha * rr[e] : alpha * rr[e] + beta * cp[e];
+      }
     }
+    if (threadIdx.x == 128) trace_mark(trace, 5);
     if (tma_c && lane == 0) bulk_wait_read<0>();  // the staging buffers outlive their last bulk store
   }
 
@@ -844,6 +896,7 @@ sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
   __syncwarp();
   cluster_sync();  // both CTAs are done with TMEM, shared memory and each other's barriers
   if (warp == 2) tmem_dealloc_2sm(tmem_base, TMEM_COLS2);
+  if (threadIdx.x == 0) trace_mark(trace, 6);
 }
 
 }  // namespace pair
@@ -943,10 +996,12 @@ int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const flo
   }
   const int pairs = g_pair_max_clusters;
   // stream-K over the partial last wave of pair tiles (see the kernel).  Unit = one accumulation
-  // chunk (K = 128, ~3.2 us of a pair); every pair must get at least one unit (contributor ranges
-  // assume no empty segment) and the shortened last wave must save clearly more than the
-  // partial-tile fix-up costs (>= 35 us and >= 3 % of the run; measured: 2304^3 159 -> 143 us,
-  // 2560^3 176 -> 158, 4096^3 548 -> 521, while a predicted saving of 26 us at 2816^3 was a 3 us loss).
+  // chunk (K = 128, ~3.2 us of a pair at nominal clocks); every pair must get at least one unit
+  // (contributor ranges assume no empty segment) and the shortened last wave must save more than
+  // the partial-tile fix-up costs.  With each CTA of a pair finishing its own half of a tile the
+  // fix-up is ~10 us: predicted savings of 26 / 29 us at 2816^3 / 3584^3 are gains of 17 / 20 us
+  // (192 -> 175, 356 -> 336), 13 us at 1792^3 is a tie and 6 us at 2048^3 a 7 us loss -- hence 15 us
+  // and >= 3 % of the run.  (One CTA reducing whole tiles cost ~35 us: 2304^3 159 -> 143 -> 118 us.)
   int sk_tiles = 0, sk_slots = 0;
   size_t sk_bytes = 0;
   const int chunks = (total_kb + KB_PER_CHUNK - 1) / KB_PER_CHUNK;
@@ -956,7 +1011,9 @@ int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const flo
     const long long seg = units / pairs;
     const double saved_us = (double)(chunks - (units + pairs - 1) / pairs) * 3.2;
     const double total_us = (double)waves(tiles2, pairs) * chunks * 3.2;
-    if (rem > 0 && seg >= 1 && saved_us >= 35.0 && saved_us >= 0.03 * total_us && rem <= ctx->num_counters) {
+    static const char* sk_env = getenv("B200_SGEMM_SK_MIN_US");  // tuning: smallest predicted saving worth the fix-up
+    const double min_saved_us = sk_env ? atof(sk_env) : 15.0;
+    if (rem > 0 && seg >= 1 && saved_us >= min_saved_us && saved_us >= 0.03 * total_us && 2 * rem <= ctx->num_counters) {
       sk_tiles = rem;
       sk_slots = (int)(chunks / seg) + 2;
       sk_bytes = (size_t)rem * (size_t)sk_slots * pair::PAIR_M * pair::PAIR_N * sizeof(float);
@@ -1041,6 +1098,45 @@ int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const flo
     B200_CUDA(cudaGetLastError());
   }
 
+  // B200_SGEMM_TRACE=1: per-CTA phase timestamps of this launch, summarised on stderr (diagnostic:
+  // synchronises the stream)
+  static const bool trace_on = getenv("B200_SGEMM_TRACE") != nullptr;
+  unsigned long long* trace = nullptr;
+  const int trace_ctas = 2 * ctx->sm_count;
+  if (trace_on) {
+    B200_CUDA(cudaMalloc((void**)&trace, sizeof(unsigned long long) * 8 * trace_ctas));
+    B200_CUDA(cudaMemsetAsync(trace, 0, sizeof(unsigned long long) * 8 * trace_ctas, ctx->compute));
+  }
+  auto trace_report = [&](const char* name, int grid) -> int {
+    if (!trace) return 0;
+    B200_CUDA(cudaStreamSynchronize(ctx->compute));
+    std::vector<unsigned long long> h((size_t)8 * grid);
+    B200_CUDA(cudaMemcpy(h.data(), trace, sizeof(unsigned long long) * 8 * grid, cudaMemcpyDeviceToHost));
+    B200_CUDA(cudaFree(trace));
+    unsigned long long t_first = ~0ull, t_last = 0;
+    for (int c = 0; c < grid; c++) {
+      if (h[c * 8 + 0] && h[c * 8 + 0] < t_first) t_first = h[c * 8 + 0];
+      if (h[c * 8 + 6] > t_last) t_last = h[c * 8 + 6];
+    }
+    static const char* phase[6] = {"setup", "first operands", "MMA issue", "last chunk ready", "epilogue stores", "drain+exit"};
+    fprintf(stderr, "[b200 sgemm trace] %s %dx%dx%d grid=%d span=%.2f us; per CTA (min / median / max us):\n", name, m, n, k, grid,
+            (double)(t_last - t_first) * 1e-3);
+    for (int p = 0; p < 6; p++) {
+      std::vector<double> d;
+      for (int c = 0; c < grid; c++)
+        if (h[c * 8 + p] && h[c * 8 + p + 1]) d.push_back(((double)h[c * 8 + p + 1] - (double)h[c * 8 + p]) * 1e-3);
+      if (d.empty()) continue;
+      std::sort(d.begin(), d.end());
+      fprintf(stderr, "    %-18s %8.2f %8.2f %8.2f   (%zu CTAs)\n", phase[p], d.front(), d[d.size() / 2], d.back(), d.size());
+    }
+    std::vector<double> e;
+    for (int c = 0; c < grid; c++)
+      if (h[c * 8]) e.push_back(((double)h[c * 8] - (double)t_first) * 1e-3);
+    std::sort(e.begin(), e.end());
+    if (!e.empty()) fprintf(stderr, "    CTA start after first CTA: median %.2f max %.2f us\n", e[e.size() / 2], e.back());
+    return 0;
+  };
+
   if (use_pair) {
     // Raster: groups of 8 m-tiles walk along n, so the ~74 tiles in flight share A and B panels in
     // L2.  With a short K there is nothing to share and the kernel is bound by the C writes: then
@@ -1052,17 +1148,17 @@ int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const flo
     if (fused)
       pair::sgemm_3xtf32_pair_kernel<true><<<grid, pair::THREADS, Rings<true>::smem_bytes(pair::EPI_WARPS), ctx->compute>>>(
           ma_hi, ma_lo, mb_hi, mb_lo, mc->c, tma_c, m, n, k, alpha, beta, C, (long long)ldc, (int)t2m, (int)t2n, raster_group,
-          sk_tiles, sk_slots, sk_partial, ctx->counters);
+          sk_tiles, sk_slots, sk_partial, ctx->counters, trace);
     else
       pair::sgemm_3xtf32_pair_kernel<false><<<grid, pair::THREADS, Rings<false>::smem_bytes(pair::EPI_WARPS), ctx->compute>>>(
           ma_hi, ma_lo, mb_hi, mb_lo, mc->c, tma_c, m, n, k, alpha, beta, C, (long long)ldc, (int)t2m, (int)t2n, raster_group,
-          sk_tiles, sk_slots, sk_partial, ctx->counters);
+          sk_tiles, sk_slots, sk_partial, ctx->counters, trace);
     B200_CUDA(cudaGetLastError());
     if (fused)
       note_launch(ctx, sk_tiles ? "sgemm_3xtf32_fused_tcgen05_pair_256x256x32_streamk" : "sgemm_3xtf32_fused_tcgen05_pair_256x256x32", 1);
     else
       note_launch(ctx, sk_tiles ? "sgemm_3xtf32_tcgen05_pair_256x256x32_streamk" : "sgemm_3xtf32_tcgen05_pair_256x256x32", 2);
-    return 0;
+    return trace_report(ctx->last_kernel, grid);
   }
   std::atomic<bool>& g_attr_done = g_attr_done_dev[ctx->device % kMaxDevices];
   if (!g_attr_done) {
@@ -1077,17 +1173,17 @@ int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const flo
   if (fused)
     sgemm_3xtf32_kernel<true><<<grid, NUM_THREADS, Rings<true>::smem_bytes(SINGLE_EPI_WARPS), ctx->compute>>>(
         ma_hi, ma_lo, mb_hi, mb_lo, mc->c, tma_c, m, n, k, alpha, beta, C, (long long)ldc, (int)t1m, (int)t1n, splits,
-        kb_per_split, partial, ctx->counters);
+        kb_per_split, partial, ctx->counters, trace);
   else
     sgemm_3xtf32_kernel<false><<<grid, NUM_THREADS, Rings<false>::smem_bytes(SINGLE_EPI_WARPS), ctx->compute>>>(
         ma_hi, ma_lo, mb_hi, mb_lo, mc->c, tma_c, m, n, k, alpha, beta, C, (long long)ldc, (int)t1m, (int)t1n, splits,
-        kb_per_split, partial, ctx->counters);
+        kb_per_split, partial, ctx->counters, trace);
   B200_CUDA(cudaGetLastError());
   if (fused)
     note_launch(ctx, splits > 1 ? "sgemm_3xtf32_fused_tcgen05_128x128x32_splitk" : "sgemm_3xtf32_fused_tcgen05_128x128x32", 1);
   else
     note_launch(ctx, splits > 1 ? "sgemm_3xtf32_tcgen05_128x128x32_splitk" : "sgemm_3xtf32_tcgen05_128x128x32", 2);
-  return 0;
+  return trace_report(ctx->last_kernel, grid);
 }
 
 // Scratch one SGEMM of this shape will need (pre-split path: the four TF32 split operands;
