@@ -995,33 +995,45 @@ int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const flo
     g_pair_attr_done = true;
   }
   const int pairs = g_pair_max_clusters;
-  // stream-K over the partial last wave of pair tiles (see the kernel).  Unit = one accumulation
-  // chunk (K = 128, ~3.2 us of a pair at nominal clocks); every pair must get at least one unit
-  // (contributor ranges assume no empty segment) and the shortened last wave must save more than
-  // the partial-tile fix-up costs.  With each CTA of a pair finishing its own half of a tile the
-  // fix-up is ~10 us: predicted savings of 26 / 29 us at 2816^3 / 3584^3 are gains of 17 / 20 us
-  // (192 -> 175, 356 -> 336), 13 us at 1792^3 is a tie and 6 us at 2048^3 a 7 us loss -- hence 15 us
-  // and >= 3 % of the run.  (One CTA reducing whole tiles cost ~35 us: 2304^3 159 -> 143 -> 118 us.)
+  // ---- pair kernel: whole tiles, or stream-K over the partial last wave (see the kernel), and pair
+  // vs single CTA.  Times in microseconds from one linear model fitted to this round's size sweeps
+  // (profiles/r2_sgemm_schedule.md): a launch costs ~2.7 us before the first MMA result; a pair
+  // spends 1.17 us per k-block of 32 (256 x 256 tile; the practical tensor rate under load), a
+  // single CTA 0.88 us (128 x 128, shared-memory bound); a split-K fix-up ~11.5 us.  Stream-K: every
+  // contributor writes a whole 256 x 256 partial per tile it touches, so the fix-up grows with the
+  // number of partials (0.13 us each: ~256 KB out and back at ~4 TB/s when all CTAs do it at
+  // once) and with the contributors ONE CTA has to add for its half tile (1.2 us each) --
+  // 2304^3 (7 leftover tiles x 12 contributors) 159 -> 118 us, 2816^3 192 -> 175, 3584^3 356 -> 336,
+  // 4096^3 523 -> 489, while 2048^3 (64 tiles, 6 us to win) and under-filled grids with short
+  // segments (1024^3: 34 us against 29 on split-K single CTAs) stay on whole tiles / single CTAs.
   int sk_tiles = 0, sk_slots = 0;
   size_t sk_bytes = 0;
   const int chunks = (total_kb + KB_PER_CHUNK - 1) / KB_PER_CHUNK;
+  constexpr double kLaunchUs = 2.7, kPairKbUs = 1.17, kSingleKbUs = 0.88, kSplitFixUs = 11.5;
+  const double t1_us = kLaunchUs + (double)waves(tiles1 * splits, P) * kb_per_split * kSingleKbUs + (splits > 1 ? kSplitFixUs : 0.0);
+  double t2_us = kLaunchUs + (double)waves(tiles2, pairs) * total_kb * kPairKbUs;
   if (ctx->opt_sgemm_streamk && tiles2 > 0) {
     const int rem = (int)(tiles2 % pairs);
     const long long units = (long long)rem * chunks;
     const long long seg = units / pairs;
-    const double saved_us = (double)(chunks - (units + pairs - 1) / pairs) * 3.2;
-    const double total_us = (double)waves(tiles2, pairs) * chunks * 3.2;
-    static const char* sk_env = getenv("B200_SGEMM_SK_MIN_US");  // tuning: smallest predicted saving worth the fix-up
-    const double min_saved_us = sk_env ? atof(sk_env) : 15.0;
-    if (rem > 0 && seg >= 1 && saved_us >= min_saved_us && saved_us >= 0.03 * total_us && 2 * rem <= ctx->num_counters) {
-      sk_tiles = rem;
-      sk_slots = (int)(chunks / seg) + 2;
-      sk_bytes = (size_t)rem * (size_t)sk_slots * pair::PAIR_M * pair::PAIR_N * sizeof(float);
+    static const char* sk_env = getenv("B200_SGEMM_SK_MIN_US");  // tuning: smallest predicted gain worth taking
+    const double min_gain_us = sk_env ? atof(sk_env) : 3.0;
+    if (rem > 0 && seg >= 1 && 2 * rem <= ctx->num_counters) {
+      const double contributors = (double)chunks / (double)seg + 1.0;
+      const double fix_us = 5.0 + std::max(0.13 * rem * contributors, 1.2 * contributors);
+      const double sk_last_kb = (double)((units + pairs - 1) / pairs) * KB_PER_CHUNK;
+      const double t2_sk = kLaunchUs + ((double)(tiles2 / pairs) * total_kb + sk_last_kb) * kPairKbUs + fix_us;
+      if (t2_us - t2_sk >= min_gain_us && t2_sk <= 0.97 * t2_us) {
+        sk_tiles = rem;
+        sk_slots = (int)(chunks / seg) + 2;
+        sk_bytes = (size_t)rem * (size_t)sk_slots * pair::PAIR_M * pair::PAIR_N * sizeof(float);
+        t2_us = t2_sk;
+      }
     }
   }
-  const double cost2 = sk_tiles ? ((double)tiles2 * total_kb / pairs) * 1536.0 + 2 * 2500.0 + 15000.0
-                                : (double)waves(tiles2, pairs) * (total_kb * 1536.0 + 2500.0);
-  bool use_pair = m >= pair::PAIR_M && n >= pair::PAIR_N && cost2 <= cost1;
+  // ties go to the single-CTA kernel (the model is ~2 us optimistic for all-stream-K grids)
+  bool use_pair = m >= pair::PAIR_M && n >= pair::PAIR_N && t2_us <= 0.95 * t1_us;
+  (void)cost1;
   if (ctx->opt_sgemm_pair == 1) use_pair = true;
   if (ctx->opt_sgemm_pair == 2) use_pair = false;
 
