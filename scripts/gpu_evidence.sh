@@ -3,9 +3,9 @@
 # traces, ncu launch lists + full captures (every command individually bounded).  usage: gpu_evidence.sh <tag>
 OUT=gpurun_out/${1:-r1p}; mkdir -p $OUT
 export OMP_NUM_THREADS=$(nproc)
-timeout 600 python -m pytest tests -x -q -m gpu > $OUT/pytest_all.txt 2>&1; echo "pytest rc=$?"; tail -2 $OUT/pytest_all.txt
+timeout 1500 python -m pytest tests -x -q -m gpu > $OUT/pytest_all.txt 2>&1; echo "pytest rc=$?"; tail -2 $OUT/pytest_all.txt
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.txt 2>&1; echo "smoke rc=$?"; tail -3 $OUT/smoke.txt
-timeout 300 python bench.py > $OUT/bench_dgemm.json 2> $OUT/bench_dgemm.err; echo "bench rc=$?"; cat $OUT/bench_dgemm.json
+timeout 600 python bench.py > $OUT/bench_dgemm.json 2> $OUT/bench_dgemm.err; echo "bench rc=$?"; cat $OUT/bench_dgemm.json
 for wl in sgemm dgemv sgemv; do
   timeout 300 python bench.py --workload $wl --no-extras > $OUT/bench_$wl.json 2> $OUT/bench_$wl.err; echo "bench $wl rc=$?"; cat $OUT/bench_$wl.json
 done
