@@ -825,10 +825,17 @@ int gemm_offload(b200_ctx* ctx, int m, int n, int k, T alpha, const T* hA, T* dA
   int nk = compute_bound ? std::max(1, std::min(8, k / 1024)) : 1;
   int kc = ((k + nk - 1) / nk + 31) / 32 * 32;
   nk = (k + kc - 1) / kc;
-  int ns = std::max(1, std::min(8, compute_bound ? n / 1024 : n / 256));
+  // column slabs of B and C: the last slab's GEMM and download are what is left exposed at the end
+  // (and B_0 is what the first block waits for), so more, narrower slabs -- as long as a slab still
+  // fills the machine (>= 512 columns: 256 DGEMM tiles with stream-K / 64 CTA-pair tiles)
+  constexpr int kMaxK = 8, kMaxS = 16, kMax = kMaxS;
+  static const char* slabs_env = getenv("B200_ENGINE_SLABS");  // tuning: upper bound on the slab count
+  // measured, 8192^3 end to end: 8 slabs 36.59 ms (DGEMM) / 11.50 (SGEMM), 12 -> 35.97 / 11.32, 16 -> 36.27 / 11.45
+  const int max_slabs = slabs_env ? std::max(1, std::min(kMaxS, atoi(slabs_env))) : 12;
+  int ns = std::max(1, std::min(max_slabs, compute_bound ? n / 512 : n / 256));
   int cols = ((n + ns - 1) / ns + 127) / 128 * 128;
   ns = (n + cols - 1) / cols;
-  constexpr int kMax = 8;
+  static_assert(kMaxK <= kMax, "array sizes");
   cudaEvent_t evA[kMax], evB[kMax], ev;
   int posA[kMax], posB[kMax];
   bool waitedA[kMax] = {}, waitedB[kMax] = {};
