@@ -289,7 +289,7 @@ int b200_ctx_create(b200_ctx** out, int device) {
   B200_CUDA(cudaEventCreate(&ctx->t1));
   if (const char* e = getenv("B200_SGEMM")) ctx->opt_sgemm = !strcmp(e, "tc") ? 1 : !strcmp(e, "ffma") ? 2 : 0;
   if (const char* e = getenv("B200_SGEMM_STREAMK")) ctx->opt_sgemm_streamk = strcmp(e, "off") != 0 && strcmp(e, "0") != 0;
-  if (const char* e = getenv("B200_SGEMM_PAIR")) ctx->opt_sgemm_pair = !strcmp(e, "on") ? 1 : !strcmp(e, "off") ? 2 : 0;
+  if (const char* e = getenv("B200_SGEMM_PAIR")) ctx->opt_sgemm_pair = !strcmp(e, "on") ? 1 : !strcmp(e, "off") ? 2 : !strcmp(e, "128") ? 3 : 0;
   if (const char* e = getenv("B200_SGEMM_TMA_STORE")) ctx->opt_sgemm_tma_store = strcmp(e, "off") != 0 && strcmp(e, "0") != 0;
   if (const char* e = getenv("B200_TALLK")) ctx->opt_tallk = strcmp(e, "off") != 0 && strcmp(e, "0") != 0;
   if (const char* e = getenv("B200_SGEMM_FUSED")) ctx->opt_sgemm_fused = !strcmp(e, "on") ? 1 : !strcmp(e, "off") ? 2 : 0;
@@ -361,7 +361,8 @@ int b200_ctx_set_option(b200_ctx* ctx, const char* key, const char* value) {
     if (!strcmp(value, "auto")) ctx->opt_sgemm_pair = 0;
     else if (!strcmp(value, "on")) ctx->opt_sgemm_pair = 1;
     else if (!strcmp(value, "off")) ctx->opt_sgemm_pair = 2;
-    else B200_REQUIRE(false, "b200_ctx_set_option: sgemm_pair must be auto|on|off, got '%s'", value);
+    else if (!strcmp(value, "128")) ctx->opt_sgemm_pair = 3;
+    else B200_REQUIRE(false, "b200_ctx_set_option: sgemm_pair must be auto|on|off|128, got '%s'", value);
     return 0;
   }
   if (!strcmp(key, "sgemm_tma_store")) {

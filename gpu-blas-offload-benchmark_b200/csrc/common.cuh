@@ -73,7 +73,7 @@ struct b200_ctx {
   // kernel-selection knobs (b200_ctx_set_option)
   int opt_sgemm = 0;       // 0 auto, 1 tc, 2 ffma
   int opt_sgemm_streamk = 1;  // CTA-pair SGEMM kernel: 1 stream-K over the partial last wave, 0 whole tiles only
-  int opt_sgemm_pair = 0;  // tcgen05 SGEMM tile config: 0 auto, 1 CTA-pair 256x256, 2 single-CTA 128x128
+  int opt_sgemm_pair = 0;  // tcgen05 SGEMM tile config: 0 auto, 1 CTA-pair 256x256, 2 single-CTA 128x128, 3 CTA-pair 256x128
   int opt_sgemm_tma_store = 1;  // tcgen05 SGEMM epilogue: 1 staged through shared memory + TMA store when C allows, 0 register stores
   int opt_sgemm_fused = 0; // 3xTF32 operand split: 0 auto, 1 fused into the GEMM (converter warps), 2 separate pre-pass
   int opt_dgemm_tile = 0;  // 0 auto, 64, 128

@@ -80,24 +80,31 @@ using namespace ptx;
 //   FUSED                      TMA lands the caller's RAW FP32 tiles in the hi ring (4 slots: TMA
 //                              latency + conversion + MMA are in flight at once) and two converter
 //                              warps write the lo ring (2 slots) from them.
-template <bool FUSED>
+template <bool FUSED, int PN = 256>
 struct Rings {
-  static constexpr int R = FUSED ? 4 : 3;
-  static constexpr int L = FUSED ? 2 : 3;
+  // PN = columns of the (pair) tile: a CTA stages PN / 2 columns of B.  The narrow pair tile
+  // (PN = 128) has 24 KB slots and spends them on a deeper raw ring: a slot is busy from the TMA
+  // issue to the end of the MMAs that read it (~2 us of load latency + conversion + MMAs), and
+  // with half the MMA time per k-block four slots in flight were not enough (measured: 0.96 us per
+  // k-block with 4 slots).
+  static constexpr uint32_t SLOT_B = A_TILE + (uint32_t)(PN / 2) * BK * 4;  // 32 KB / 24 KB
+  static constexpr int R = FUSED ? (PN == 128 ? 6 : 4) : (PN == 128 ? 4 : 3);
+  static constexpr int L = FUSED ? 2 : R;
   // + 4 KB per epilogue warp: the staging buffers of the TMA-store epilogue (store_rows_tma)
   static constexpr uint32_t smem_bytes(int epi_warps) {
-    return (uint32_t)(R + L) * SLOT + 1024 /*align*/ + 256 /*barriers*/ + (uint32_t)epi_warps * STAGING_PER_WARP;
+    return (uint32_t)(R + L) * SLOT_B + 1024 /*align*/ + 256 /*barriers*/ + (uint32_t)epi_warps * STAGING_PER_WARP;
   }
   static_assert(8 * (2 * R + 2 * L + 2 * ACC_STAGES + 1) <= 256, "barrier area");
+  static_assert(SLOT_B % 1024 == 0, "SWIZZLE_128B atoms need 1024-byte aligned tiles");
   uint32_t base, bars;
   __device__ explicit Rings(const uint8_t* smem_raw) {
     base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-byte alignment
-    bars = base + (uint32_t)(R + L) * SLOT;
+    bars = base + (uint32_t)(R + L) * SLOT_B;
   }
   __device__ uint32_t staging(int epi_warp) const { return bars + 256u + (uint32_t)epi_warp * STAGING_PER_WARP; }
-  __device__ uint32_t a_hi(int r) const { return base + (uint32_t)r * SLOT; }
+  __device__ uint32_t a_hi(int r) const { return base + (uint32_t)r * SLOT_B; }
   __device__ uint32_t b_hi(int r) const { return a_hi(r) + A_TILE; }
-  __device__ uint32_t a_lo(int l) const { return base + (uint32_t)(R + l) * SLOT; }
+  __device__ uint32_t a_lo(int l) const { return base + (uint32_t)(R + l) * SLOT_B; }
   __device__ uint32_t b_lo(int l) const { return a_lo(l) + A_TILE; }
   // hi_full: TMA bytes have landed (pre-split: of all four tiles); hi_empty / lo_empty: the MMAs that
   // read the slot are done; lo_full (FUSED): the converter warps have written the slot
@@ -193,9 +200,11 @@ __device__ __forceinline__ float tf32_lo(float x) {
 // four 16-byte words, software-pipelined by hand: the loads of batch b + 1 are in flight while
 // batch b is converted and stored (the asm statements are volatile, so the order written here is
 // the order issued -- a plain unrolled loop serialised load -> convert -> store on one register set).
+template <uint32_t BYTES = SLOT>
 __device__ __forceinline__ void convert_slot(uint32_t src, uint32_t dst, int t) {
   constexpr uint32_t STEP = 64u * 16u;  // a warp touches 512 consecutive bytes: conflict-free
-  constexpr int U = 4, BATCHES = (int)(SLOT / STEP) / U;
+  constexpr int U = 4, BATCHES = (int)(BYTES / STEP) / U;
+  static_assert(BYTES % (STEP * U) == 0, "whole batches");
   const uint32_t s0 = src + (uint32_t)t * 16u, d0 = dst + (uint32_t)t * 16u;
   float4 cur[U], nxt[U];
 #pragma unroll
@@ -567,16 +576,16 @@ namespace pair {
 
 constexpr int CTA_M = 128;            // rows of A and C per CTA
 constexpr int PAIR_M = 2 * CTA_M;     // UMMA M
-constexpr int PAIR_N = 256;           // UMMA N
-constexpr int CTA_N = PAIR_N / 2;     // columns of B each CTA stages
+constexpr int PAIR_N = 256;           // UMMA N of the large-problem configuration (template default)
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = 128 + 32 * EPI_WARPS;
-constexpr uint32_t TMEM_COLS2 = ACC_STAGES * PAIR_N;  // 512
-static_assert(CTA_M * BK * 4 == A_TILE && CTA_N * BK * 4 == B_TILE, "the pair kernel shares Rings<> with the single-CTA kernel");
-constexpr uint32_t kIdesc2 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (0u << 16) |
-                             ((uint32_t)(PAIR_N >> 3) << 17) | ((uint32_t)(PAIR_M >> 4) << 24);
+static_assert(CTA_M * BK * 4 == A_TILE && (PAIR_N / 2) * BK * 4 == B_TILE, "the pair kernel shares Rings<> with the single-CTA kernel");
+// PN = UMMA N = columns of a pair tile.  256: the large-problem tile.  128: the mid-size tile --
+// twice as many tiles for the same problem (1536^3: 72 instead of 36 on 74 pairs), each CTA stages
+// 64 columns of B (8 KB of the 16 KB B part of a ring slot), 6 KB of operand reads per UMMA
+// instead of the single-CTA kernel's 8 KB for half the work.
 
-template <bool FUSED>
+template <bool FUSED, int PN = PAIR_N>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                          const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -585,8 +594,14 @@ sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
                          int tiles_m, int tiles_n, int raster_group, int sk_tiles, int sk_slots,
                          float* __restrict__ partial, unsigned int* __restrict__ counters,
                          unsigned long long* __restrict__ trace) {
-  using RG = Rings<FUSED>;
+  using RG = Rings<FUSED, PN>;
   constexpr int R = RG::R, L = RG::L;
+  constexpr int PAIR_N = PN;            // shadows the namespace constant: this instantiation's UMMA N
+  constexpr int CTA_N = PN / 2;         // columns of B each CTA stages = accumulator columns per epilogue warp
+  constexpr uint32_t TMEM_COLS2 = ACC_STAGES * PN;  // 512 / 256
+  constexpr uint32_t SLOT_USED = RG::SLOT_B;  // bytes of a ring slot: 16 KB of A + CTA_N columns of B
+  constexpr uint32_t kIdesc2 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (0u << 16) |
+                               ((uint32_t)(PN >> 3) << 17) | ((uint32_t)(PAIR_M >> 4) << 24);
   extern __shared__ uint8_t smem_raw[];
   __shared__ int s_is_last;
   const RG rg(smem_raw);
@@ -686,7 +701,7 @@ sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
           if (FUSED) {
             const uint32_t bar = rg.hi_full(r.i);
             if (elected) {
-              mbar_expect_tx(bar, SLOT);
+              mbar_expect_tx(bar, SLOT_USED);
 #pragma unroll
               for (int c = 0; c < CTA_M / 32; c++) tma_load_2d(rg.a_hi(r.i) + c * 4096, &map_a_hi, bar, my_m + c * 32, kb * BK);
               tma_load_2d(rg.b_hi(r.i), &map_b_hi, bar, kb * BK, my_n);
@@ -695,7 +710,7 @@ sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
           } else {
             const uint32_t lbar = mapa_shared(rg.hi_full(r.i), 0);
             if (elected) {
-              if (rank == 0) mbar_expect_tx(rg.hi_full(r.i), 4 * SLOT);
+              if (rank == 0) mbar_expect_tx(rg.hi_full(r.i), 4 * SLOT_USED);
 #pragma unroll
               for (int c = 0; c < CTA_M / 32; c++) {
                 tma_load_2d_2sm(rg.a_hi(r.i) + c * 4096, &map_a_hi, lbar, my_m + c * 32, kb * BK);
@@ -778,7 +793,7 @@ sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
         for (int kb = w.c0 * KB_PER_CHUNK; kb < kb_hi; kb++) {
           mbar_wait(rg.hi_full(r.i), r.ph);
           mbar_wait(rg.lo_empty(l.i), l.ph ^ 1);
-          convert_slot(rg.a_hi(r.i), rg.a_lo(l.i), ct);
+          convert_slot<SLOT_USED>(rg.a_hi(r.i), rg.a_lo(l.i), ct);
           fence_proxy_async_smem();
           __syncwarp();
           // what must be ordered before the leader's MMAs are this warp's shared-memory stores, and
@@ -866,6 +881,7 @@ sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
       const int hrow = (int)rank * CTA_M + rg4 * 4;  // row inside the tile
       const int row0 = m0 + hrow;
       const int cbase = cg * 32;
+      if (cbase >= PAIR_N) continue;  // PN = 128: half of the column groups have nothing to add
       float4 tot[32];
 #pragma unroll
       for (int j = 0; j < 32; j++) tot[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -913,7 +929,7 @@ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // calls encode them once; the multi-GPU engine walks a handful of K-chunks of A per step.
 struct MapSet {
   const void *pa = nullptr, *pb = nullptr;  // what a_hi / b_hi describe
-  int device = -1, m = -1, n = -1, k = -1, lda = -1, ldb = -1;
+  int device = -1, m = -1, n = -1, k = -1, lda = -1, ldb = -1, b_box = -1;
   bool fused = false;
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
   const void* pc = nullptr;  // what `c` describes (the TMA-store epilogue), nullptr: not encoded
@@ -922,16 +938,18 @@ struct MapSet {
 };
 constexpr int kMapSets = 8;
 
-}  // namespace
+// Everything sgemm_tc_dispatch decides before it touches memory -- tile configuration, k-splits,
+// stream-K, fused or pre-split operands, scratch -- in one place, so that b200_sgemm_prepare
+// reserves exactly the scratch the call will use (a workspace that grows inside the caller's timed
+// region costs milliseconds).
+struct SgemmPlan {
+  long long t1m, t1n, tiles1, t2m, t2n, tiles2, t3n, tiles3;
+  int total_kb, pairs, splits, kb_per_split, sk_tiles, sk_slots, pair_n;
+  bool use_pair, fused;
+  size_t part_bytes, sk_bytes, need, countA, countB, offAlo, offBhi, offBlo;
+};
 
-int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const float* A, int lda,
-                      const float* B, int ldb, float beta, float* C, int ldc) {
-  if (ctx->opt_sgemm == 2) return -1;  // "ffma" forces the SIMT path, "tc" forces this one
-  const bool forced = ctx->opt_sgemm == 1;
-  if ((lda % 4) || (ldb % 4) || ((uintptr_t)A % 16) || ((uintptr_t)B % 16)) return -1;
-  // below ~512^3 the launch and the descriptor encodes cost more than the FFMA path's single
-  // launch (measured crossover, size_sweep.py)
-  if (!forced && ((double)m * n * k < 1.0e8 || m < 64 || n < 64)) return -1;
+int plan_sgemm(b200_ctx* ctx, int m, int n, int k, int lda, int ldb, SgemmPlan* out) {
   // ---- schedule: CTA pairs on 256 x 256 tiles, or single CTAs on 128 x 128 tiles cut into
   // `splits` k ranges.  Both are persistent, so time = waves x time per work item; the cost
   // model below is in tensor-pipe clocks per k-block of 32 (pair UMMA 256x256x8: 128 clk x 12 =
@@ -989,8 +1007,10 @@ int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const flo
       pairs_min = std::min(pairs_min, clusters);
       return 0;
     };
-    if (setup(pair::sgemm_3xtf32_pair_kernel<false>, Rings<false>::smem_bytes(pair::EPI_WARPS))) return 1;
-    if (setup(pair::sgemm_3xtf32_pair_kernel<true>, Rings<true>::smem_bytes(pair::EPI_WARPS))) return 1;
+    if (setup(pair::sgemm_3xtf32_pair_kernel<false, 256>, Rings<false>::smem_bytes(pair::EPI_WARPS))) return 1;
+    if (setup(pair::sgemm_3xtf32_pair_kernel<true, 256>, Rings<true>::smem_bytes(pair::EPI_WARPS))) return 1;
+    if (setup(pair::sgemm_3xtf32_pair_kernel<false, 128>, Rings<false, 128>::smem_bytes(pair::EPI_WARPS))) return 1;
+    if (setup(pair::sgemm_3xtf32_pair_kernel<true, 128>, Rings<true, 128>::smem_bytes(pair::EPI_WARPS))) return 1;
     g_pair_max_clusters = pairs_min;
     g_pair_attr_done = true;
   }
@@ -1034,8 +1054,29 @@ int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const flo
   // ties go to the single-CTA kernel (the model is ~2 us optimistic for all-stream-K grids)
   bool use_pair = m >= pair::PAIR_M && n >= pair::PAIR_N && t2_us <= 0.95 * t1_us;
   (void)cost1;
-  if (ctx->opt_sgemm_pair == 1) use_pair = true;
+  // ... and the mid-size pair tile 256 x 128 (whole tiles only): per k-block it is bound by shared
+  // memory (144 KB per CTA: 72 KB of operand reads, 24 KB landed by TMA, 48 KB through the
+  // converters) at ~0.63 us for HALF the work of the 256 x 256 tile, but it has twice the tiles --
+  // what problems between ~1000^3 and ~1700^3 need to fill 74 pairs.
+  // It runs on PRE-SPLIT operands: with the converters in the loop the same tile measured 0.82-0.96 us
+  // per k-block whatever the ring depth or the polling of the other warps (1536^3: 47.5-48.9 us fused,
+  // 41.4 pre-split including the split pass; 1280^3 39.9-41.6 vs 35.2), so the split pass
+  // (~2.5 us + 0.3 us per MB of A and B) is part of its price.
+  constexpr double kPair128KbUs = 0.64;
+  const size_t countA = (size_t)lda * (k - 1) + m, countB = (size_t)ldb * (n - 1) + k;
+  const double split_pass_us = 2.5 + 0.3e-6 * 4.0 * (double)(countA + countB);
+  const long long t3n = (n + 127) / 128, tiles3 = t2m * t3n;
+  const double t3_us = kLaunchUs + (double)waves(tiles3, pairs) * total_kb * kPair128KbUs +
+                       (ctx->opt_sgemm_fused == 1 ? 0.3 * total_kb * kPair128KbUs : split_pass_us);
+  int pair_n = pair::PAIR_N;
+  if (m >= pair::PAIR_M && n >= 128 && t3_us <= 0.95 * std::min(t1_us, use_pair ? t2_us : t1_us)) {
+    use_pair = true;
+    pair_n = 128;
+  }
+  if (ctx->opt_sgemm_pair == 1) { use_pair = true; pair_n = pair::PAIR_N; }
   if (ctx->opt_sgemm_pair == 2) use_pair = false;
+  if (ctx->opt_sgemm_pair == 3) { use_pair = true; pair_n = 128; }
+  if (use_pair && pair_n == 128) { sk_tiles = 0; sk_slots = 0; sk_bytes = 0; }  // whole tiles only
 
   // ---- operand split: fused into the GEMM (converter warps: one launch, no hi/lo copies in HBM)
   // or a separate pass writing hi/lo copies into the workspace.  Fused wins wherever the launch
@@ -1046,11 +1087,36 @@ int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const flo
   // 128 B/clk) and the converters' traffic comes on top (1280^3 41.7 vs 38.3 us, 1536^3 49.6 vs 45.4).
   bool fused = ctx->opt_sgemm_fused != 2;
   if (ctx->opt_sgemm_fused == 0 && !use_pair && splits == 1 && total_kb >= 32) fused = false;
+  if (ctx->opt_sgemm_fused == 0 && use_pair && pair_n == 128) fused = false;
 
-  const size_t countA = (size_t)lda * (k - 1) + m, countB = (size_t)ldb * (n - 1) + k;
   const size_t offAlo = align_up(countA * 4, 1024), offBhi = 2 * offAlo;
   const size_t offBlo = offBhi + align_up(countB * 4, 1024);
   const size_t need = fused ? 0 : offBlo + align_up(countB * 4, 1024);
+  *out = SgemmPlan{t1m, t1n, tiles1, t2m, t2n, tiles2, t3n, tiles3, total_kb, pairs, splits, kb_per_split, sk_tiles, sk_slots,
+                   pair_n, use_pair, fused, part_bytes, sk_bytes, need, countA, countB, offAlo, offBhi, offBlo};
+  return 0;
+}
+
+}  // namespace
+
+int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const float* A, int lda,
+                      const float* B, int ldb, float beta, float* C, int ldc) {
+  if (ctx->opt_sgemm == 2) return -1;  // "ffma" forces the SIMT path, "tc" forces this one
+  const bool forced = ctx->opt_sgemm == 1;
+  if ((lda % 4) || (ldb % 4) || ((uintptr_t)A % 16) || ((uintptr_t)B % 16)) return -1;
+  // below ~512^3 the launch and the descriptor encodes cost more than the FFMA path's single
+  // launch (measured crossover, size_sweep.py)
+  if (!forced && ((double)m * n * k < 1.0e8 || m < 64 || n < 64)) return -1;
+  SgemmPlan plan;
+  if (const int rc = plan_sgemm(ctx, m, n, k, lda, ldb, &plan)) return rc;
+  const long long t1m = plan.t1m, t1n = plan.t1n, tiles1 = plan.tiles1, t2m = plan.t2m, t2n = plan.t2n, tiles2 = plan.tiles2,
+                  t3n = plan.t3n, tiles3 = plan.tiles3;
+  const int total_kb = plan.total_kb, pairs = plan.pairs, splits = plan.splits, kb_per_split = plan.kb_per_split,
+            sk_tiles = plan.sk_tiles, sk_slots = plan.sk_slots, pair_n = plan.pair_n;
+  const bool use_pair = plan.use_pair, fused = plan.fused;
+  const size_t part_bytes = plan.part_bytes, sk_bytes = plan.sk_bytes, need = plan.need, countA = plan.countA,
+               countB = plan.countB, offAlo = plan.offAlo, offBhi = plan.offBhi, offBlo = plan.offBlo;
+  (void)total_kb; (void)t1n; (void)t2n;
   // room for the pair kernel's stream-K slots: rem tiles x (pairs / rem + 2) contributors x 256 KB
   // = (pairs + 2 rem) x 256 KB <= 56 MB whatever the problem size; the context reserves that much
   // when it is created (and b200_sgemm_prepare the pre-split copies), so that this call does not
@@ -1063,13 +1129,14 @@ int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const flo
   const float* pa = fused ? A : a_hi;  // what the hi maps describe
   const float* pb = fused ? B : b_hi;
 
+  const int b_box = (use_pair && pair_n == 128) ? 64 : BN;  // columns of B per TMA box = per CTA
   static thread_local MapSet sets[kMapSets];
   static thread_local int next_set = 0;
   MapSet* mc = nullptr;
   for (int i = 0; i < kMapSets; i++) {
     MapSet& s = sets[i];
     if (s.pa == pa && s.pb == pb && s.device == ctx->device && s.fused == fused && s.m == m && s.n == n && s.k == k &&
-        s.lda == lda && s.ldb == ldb) {
+        s.lda == lda && s.ldb == ldb && s.b_box == b_box) {
       mc = &s;
       break;
     }
@@ -1080,16 +1147,16 @@ int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const flo
     mc->pa = nullptr;
     mc->pc = nullptr;
     if (make_tensor_map_2d(&mc->a_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, pa, m, k, (uint64_t)lda * 4, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 2;
-    if (make_tensor_map_2d(&mc->b_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, pb, k, n, (uint64_t)ldb * 4, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B)) return 2;
+    if (make_tensor_map_2d(&mc->b_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, pb, k, n, (uint64_t)ldb * 4, BK, b_box, CU_TENSOR_MAP_SWIZZLE_128B)) return 2;
     if (fused) {
       mc->a_lo = mc->a_hi;
       mc->b_lo = mc->b_hi;
     } else {
       if (make_tensor_map_2d(&mc->a_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, a_lo, m, k, (uint64_t)lda * 4, 32, BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 2;
-      if (make_tensor_map_2d(&mc->b_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, b_lo, k, n, (uint64_t)ldb * 4, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B)) return 2;
+      if (make_tensor_map_2d(&mc->b_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, b_lo, k, n, (uint64_t)ldb * 4, BK, b_box, CU_TENSOR_MAP_SWIZZLE_128B)) return 2;
     }
     mc->pa = pa; mc->pb = pb; mc->device = ctx->device; mc->fused = fused;
-    mc->m = m; mc->n = n; mc->k = k; mc->lda = lda; mc->ldb = ldb;
+    mc->m = m; mc->n = n; mc->k = k; mc->lda = lda; mc->ldb = ldb; mc->b_box = b_box;
   }
   const CUtensorMap &ma_hi = mc->a_hi, &ma_lo = mc->a_lo, &mb_hi = mc->b_hi, &mb_lo = mc->b_lo;
   // TMA-store epilogue: whole tiles of a beta == 0 call whose C obeys TMA's alignment rules
@@ -1156,17 +1223,23 @@ int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const flo
     // contiguous in DRAM (M = N = 8192, K = 32: 58.1 -> 51.0 us; at K = 8192 the same order costs 3 %).
     static const char* rg_env = getenv("B200_SGEMM_RASTER");  // tuning: m-tiles per raster group
     const int raster_group = rg_env ? std::max(1, atoi(rg_env)) : (k <= 256 ? std::max(8, (int)t2m) : 8);
-    const int grid = 2 * (int)(sk_tiles ? pairs : std::min<long long>(tiles2, pairs));
-    if (fused)
-      pair::sgemm_3xtf32_pair_kernel<true><<<grid, pair::THREADS, Rings<true>::smem_bytes(pair::EPI_WARPS), ctx->compute>>>(
-          ma_hi, ma_lo, mb_hi, mb_lo, mc->c, tma_c, m, n, k, alpha, beta, C, (long long)ldc, (int)t2m, (int)t2n, raster_group,
-          sk_tiles, sk_slots, sk_partial, ctx->counters, trace);
-    else
-      pair::sgemm_3xtf32_pair_kernel<false><<<grid, pair::THREADS, Rings<false>::smem_bytes(pair::EPI_WARPS), ctx->compute>>>(
-          ma_hi, ma_lo, mb_hi, mb_lo, mc->c, tma_c, m, n, k, alpha, beta, C, (long long)ldc, (int)t2m, (int)t2n, raster_group,
-          sk_tiles, sk_slots, sk_partial, ctx->counters, trace);
+    const bool narrow = pair_n == 128;
+    const long long ptiles = narrow ? tiles3 : tiles2;
+    const int ptn = (int)(narrow ? t3n : t2n);
+    const int grid = 2 * (int)(sk_tiles ? pairs : std::min<long long>(ptiles, pairs));
+#define B200_PAIR_LAUNCH(F, PN)                                                                                        \
+  pair::sgemm_3xtf32_pair_kernel<F, PN><<<grid, pair::THREADS, Rings<F, PN>::smem_bytes(pair::EPI_WARPS), ctx->compute>>>( \
+      ma_hi, ma_lo, mb_hi, mb_lo, mc->c, tma_c, m, n, k, alpha, beta, C, (long long)ldc, (int)t2m, ptn, raster_group,  \
+      sk_tiles, sk_slots, sk_partial, ctx->counters, trace)
+    if (fused && narrow) B200_PAIR_LAUNCH(true, 128);
+    else if (fused) B200_PAIR_LAUNCH(true, 256);
+    else if (narrow) B200_PAIR_LAUNCH(false, 128);
+    else B200_PAIR_LAUNCH(false, 256);
+#undef B200_PAIR_LAUNCH
     B200_CUDA(cudaGetLastError());
-    if (fused)
+    if (narrow)
+      note_launch(ctx, fused ? "sgemm_3xtf32_fused_tcgen05_pair_256x128x32" : "sgemm_3xtf32_tcgen05_pair_256x128x32", fused ? 1 : 2);
+    else if (fused)
       note_launch(ctx, sk_tiles ? "sgemm_3xtf32_fused_tcgen05_pair_256x256x32_streamk" : "sgemm_3xtf32_fused_tcgen05_pair_256x256x32", 1);
     else
       note_launch(ctx, sk_tiles ? "sgemm_3xtf32_tcgen05_pair_256x256x32_streamk" : "sgemm_3xtf32_tcgen05_pair_256x256x32", 2);
@@ -1198,17 +1271,15 @@ int sgemm_tc_dispatch(b200_ctx* ctx, int m, int n, int k, float alpha, const flo
   return trace_report(ctx->last_kernel, grid);
 }
 
-// Scratch one SGEMM of this shape will need (pre-split path: the four TF32 split operands;
+// Scratch one SGEMM of this shape will need (pre-split schedules: the four TF32 split operands;
 // always: partial-tile room), reserved outside the caller's timed region.
 int sgemm_tc_prepare(b200_ctx* ctx, int m, int n, int k, int lda, int ldb) {
   if (ctx->opt_sgemm == 2 || (lda % 4) || (ldb % 4) || m < 64 || n < 64 || k < 1) return 0;
   if (ctx->opt_sgemm != 1 && (double)m * n * k < 1.0e8) return 0;
-  size_t need = 0;
-  if (ctx->opt_sgemm_fused == 2) {
-    const size_t countA = (size_t)lda * (k - 1) + m, countB = (size_t)ldb * (n - 1) + k;
-    need = 2 * align_up(countA * 4, 1024) + 2 * align_up(countB * 4, 1024);
-  }
-  return ensure_workspace(ctx, need + ((size_t)64 << 20));
+  SgemmPlan plan;
+  const int rc = plan_sgemm(ctx, m, n, k, lda, ldb, &plan);
+  if (rc) return rc < 0 ? 0 : rc;
+  return ensure_workspace(ctx, plan.need + std::max(std::max(plan.part_bytes, plan.sk_bytes), (size_t)64 << 20));
 }
 
 }  // namespace b200

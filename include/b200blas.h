@@ -66,7 +66,8 @@ int b200_ctx_device(const b200_ctx* ctx, int* device, int* sm_count);
  *   "dgemm_tma"  = "on" | "off"   (large aligned DGEMM: TMA-fed kernel vs cp.async kernel)
  *   "dgemm_streamk" = "on" | "off" (TMA kernel: stream-K over the partial last wave of tiles)
  *   "sgemm_streamk" = "on" | "off" (CTA-pair SGEMM kernel: stream-K over the partial last wave of tiles)
- *   "sgemm_pair" = "auto" | "on" | "off" (tcgen05 SGEMM: CTA-pair 256x256 tiles vs single-CTA 128x128)
+ *   "sgemm_pair" = "auto" | "on" | "off" | "128" (tcgen05 SGEMM: CTA-pair 256x256 tiles, single-CTA 128x128,
+ *                  CTA-pair 256x128 tiles)
  *   "sgemm_fused" = "auto" | "on" | "off" (3xTF32 operand split: fused into the GEMM -- TMA lands the raw
  *                  FP32 tiles, converter warps write the lo parts -- vs a separate pre-pass that writes
  *                  hi/lo copies of A and B into the workspace)

@@ -220,3 +220,53 @@ def test_sgemm_tma_store_epilogue_matches_register_stores(blob, ctx, oracle, sha
     assert np.all(got_tma.reshape(n, ldc)[:, m:] == -7.0)
     want = oracle.harness_gemm("f32", m, n, k)
     assert max_rel_err(got_tma.reshape(n, ldc)[:, :m].ravel(), want) <= 1e-5
+
+
+# ---- mid-size CTA-pair tile 256 x 128 (cta_group::2, UMMA N = 128), forced ---------------------
+PAIR128_SHAPES = [
+    (256, 128, 32), (256, 256, 256), (512, 384, 96), (768, 1280, 1000), (260, 300, 200), (1028, 516, 260),
+    (1024, 1024, 1024), (1536, 1536, 1536), (300, 2304, 72), (2052, 1028, 516), (256, 128, 32768), (1280, 1152, 2052),
+]
+
+
+@pytest.fixture
+def force_pair128(ctx):
+    ctx.set_option("sgemm_pair", "128")
+    yield
+    ctx.set_option("sgemm_pair", "auto")
+
+
+@pytest.mark.parametrize("shape", PAIR128_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_sgemm_pair128_kernel(blob, ctx, oracle, force_pair128, shape):
+    m, n, k = shape
+    A, B, _ = oracle.init_gemm("f32", m, n, k)
+    want = oracle.harness_gemm("f32", m, n, k)
+    got, kern = run_gemm(blob, ctx, "f32", "once", m, n, k, A, B, iters=2)
+    assert "pair_256x128" in kern, kern
+    err = max_rel_err(got, want)
+    assert err <= 1e-5, (shape, kern, err)
+
+
+def test_sgemm_pair128_alpha_beta_ld_and_bitwise_vs_single_cta(blob, ctx, oracle, force_pair128):
+    rng = np.random.default_rng(14)
+    m, n, k = 700, 520, 200
+    lda, ldb, ldc = 704, 200, 701
+    A = rng.random(lda * k).astype(np.float32)
+    B = rng.random(ldb * n).astype(np.float32)
+    C0 = rng.random(ldc * n).astype(np.float32)
+    want = C0.copy()
+    oracle.gemm("f32", m, n, k, 1.5, A, lda, B, ldb, 0.5, want, ldc)
+    got, kern = run_gemm(blob, ctx, "f32", "once", m, n, k, A, B, C0=C0, alpha=1.5, beta=0.5,
+                         lda=lda, ldb=ldb, ldc=ldc)
+    assert "pair_256x128" in kern, kern
+    assert max_rel_err(got, want) <= 1e-5
+    # same products, same chunked accumulation order as the other tile shapes: identical bits
+    m, n, k = 2048, 1536, 264
+    A, B, _ = oracle.init_gemm("f32", m, n, k)
+    got3, kern3 = run_gemm(blob, ctx, "f32", "once", m, n, k, A, B)
+    ctx.set_option("sgemm_pair", "off")
+    got1, kern1 = run_gemm(blob, ctx, "f32", "once", m, n, k, A, B)
+    ctx.set_option("sgemm_pair", "on")
+    got2, kern2 = run_gemm(blob, ctx, "f32", "once", m, n, k, A, B)
+    assert "256x128" in kern3 and kern1.endswith("128x128x32") and "256x256" in kern2, (kern1, kern2, kern3)
+    assert np.array_equal(got3, got1) and np.array_equal(got3, got2)
