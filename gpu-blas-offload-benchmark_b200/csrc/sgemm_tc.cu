@@ -8,15 +8,20 @@
 // (TMA's global-stride rule); everything else takes the FFMA path in
 // gemm_simt.cu.
 //
-// Numerics.  TF32 keeps 11 significand bits, FP32 24.  Each operand is split
-// once per call into  x = hi + lo,  hi = round-to-nearest-TF32(x) (low 13 bits
-// zero, so the tensor core's own truncation is the identity on it) and
-// lo = x - hi (exact in FP32), and the product is formed as
+// Numerics.  TF32 keeps 11 significand bits, FP32 24.  Each operand is split into
+// x = hi + lo and the product is formed as
 //     A*B ~= A_lo*B_hi + A_hi*B_lo + A_hi*B_hi          (3 tensor-core MMAs)
-// the dropped lo*lo term and the truncation of lo to 11 bits are each <= 2^-21
-// relative.  The tensor core's FP32 accumulate truncates (measured bias ~7e-8
-// per K=8 step), so TMEM accumulates only 128 of K at a time and the epilogue
-// warps sum those chunks in round-to-nearest FP32 registers (bar: 1e-5).
+// Two ways to get hi and lo (chosen per call by plan_sgemm):
+//   fused      TMA lands the RAW FP32 tile; the tensor core reads only the top 19 bits of a word,
+//              so the raw word is hi = trunc_tf32(x), and two converter warps write
+//              lo = RN_tf32(x - hi) (the subtraction is exact) into a second shared-memory ring.
+//              One launch, no copies of A and B in HBM.
+//   pre-split  one pass (split_tf32_kernel) writes hi = RN_tf32(x), lo = x - hi into the
+//              workspace; the GEMM loads both by TMA.
+// The dropped lo*lo term and the rounding of lo to 11 bits are each <= 2^-20 relative.  The
+// tensor core's FP32 accumulate truncates (measured bias ~7e-8 per K=8 step), so TMEM
+// accumulates only 128 of K at a time and the epilogue warps sum those chunks in
+// round-to-nearest FP32 registers (bar: 1e-5; measured 1.7e-6 ... 2.7e-6 on the harness data).
 //
 // Layout.  Column-major operands map onto UMMA without any transposition:
 //   A (M x K, M contiguous)  = "MN-major" A: TMA boxes of {32 m, 32 k} land as
@@ -31,18 +36,20 @@
 //       8 n; successive K=8 MMAs advance the start address by 32 bytes)
 //   D (TMEM) has the 128 tile rows on the 128 lanes, so tcgen05.ld 32x32b gives
 //       thread t row t: a warp's store of one column is 32 consecutive floats
-//       of column-major C -- coalesced with no shared-memory staging.
+//       of column-major C -- coalesced from registers, and a conflict-free [column][32 rows]
+//       staging layout for the TMA-store epilogue.
 //
-// Two kernels share the layouts above:
-//   sgemm_3xtf32_pair_kernel  CTA pairs (cta_group::2), UMMA 256x256x8 -- the large-problem
+// Two kernels, three tile shapes, share the layouts above:
+//   sgemm_3xtf32_pair_kernel<FUSED, 256>  CTA pairs (cta_group::2), UMMA 256x256x8 -- the large-problem
 //                             kernel, described at its definition below
-//   sgemm_3xtf32_kernel       single CTA, UMMA 128x128x8, persistent over (tile, k-split) work
-//                             items, 256 threads:
-//     warp 0  TMA producer      warp 1  MMA issuer (one elected lane)
-//     warp 2  TMEM allocator    warps 4-7  epilogue (TMEM -> registers -> C, or -> split-K
-//                                          partial + last-arriver reduction)
-//   3 smem stages x {A_hi, A_lo, B_hi, B_lo} 16 KB tiles, 2 TMEM accumulator stages so the
-//   epilogue of chunk i overlaps the MMAs of chunk i+1.
+//   sgemm_3xtf32_pair_kernel<FUSED, 128>  the same with UMMA 256x128x8: twice the tiles for mid sizes
+//   sgemm_3xtf32_kernel<FUSED>            single CTA, UMMA 128x128x8, persistent over (tile, k-split)
+//                             work items, 256 threads:
+//     warp 0  TMA producer      warp 1  MMA issuer   (warp-uniform loops, one elected lane issues)
+//     warps 2-3  converters (FUSED; warp 2 also allocates TMEM)
+//     warps 4-7  epilogue (TMEM -> registers -> shared-memory staging -> TMA store, or -> split-K
+//                partial + last-arriver reduction)
+//   2 TMEM accumulator stages so the epilogue of chunk i overlaps the MMAs of chunk i+1.
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
