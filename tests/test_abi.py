@@ -51,6 +51,14 @@ def test_sass_is_sm100a_native(blob):
     assert "sm_100a" in out.stdout
     sass = subprocess.run(["cuobjdump", "-sass", blob.LIB_PATH], capture_output=True, text=True).stdout
     assert "DMMA" in sass
+    # the Blackwell machinery the kernels are written for, by SASS mnemonic (profiles/r2_sass_mnemonics.txt):
+    # tcgen05.mma / tcgen05.ld / tcgen05.commit, TMA load and TMA store, mbarrier, cluster barrier
+    # (CTA pairs, tall-K clusters), setmaxnreg, elect.sync
+    for mnemonic in ("UTCHMMA", "LDTM", "UTCBAR", "UTMALDG", "UTMASTG", "SYNCS", "UCGABAR_ARV", "USETMAXREG", "ELECT"):
+        assert mnemonic in sass, mnemonic
+    # ... and no library GEMM: the product links cudart only
+    ldd = subprocess.run(["ldd", blob.LIB_PATH], capture_output=True, text=True).stdout
+    assert "cublas" not in ldd.lower() and "cutlass" not in ldd.lower(), ldd
 
 
 def test_no_gpu_means_loud_failure_not_cpu_fallback(blob):
